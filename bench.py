@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Fock builds/s (J+K) of the B200-native path on BASELINE.json's headline config:
+synthetic UHF n_bf=256, full fp64 ERI (34.36 GB) resident in HBM, alpha/beta J+K from one
+ERI pass.  One "step" = one `add_2e_term!`-equivalent call (scfb_fock_jk*), the
+cross-GPU allreduce included when N > 1.
+
+  python bench.py [--gpus N --steps K --warmup W]          ours (under torchrun for N > 1)
+  python bench.py --impl reference ...                     the reference's CPU strategy
+                                                           (oracle port; rank 0 only)
+Prints ONE JSON line (rank 0).  The inputs (34 GB) are far larger than the 126 MB L2, so
+no explicit L2 flush is needed between timed iterations (config.l2_policy says so).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fock_builds_per_s"
+UNIT = "Fock builds/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=100)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--n-bas", type=int, default=256)
+    p.add_argument("--n-spin", type=int, default=2, choices=[1, 2])
+    p.add_argument("--layout", default="full", choices=["full", "packed8"])
+    p.add_argument("--cpu-slabs", type=int, default=4, help="nu-slabs in the CPU baseline sample")
+    p.add_argument("--cpu-steps", type=int, default=3)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
+    return p.parse_args()
+
+
+def workload_name(a):
+    spin = "UHF" if a.n_spin == 2 else "RHF"
+    return f"synthetic {spin} n_bf={a.n_bas}, {a.layout} fp64 ERI ({8 * a.n_bas ** 4 / 1e9:.2f} GB), hash family"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- nvidia-smi clock sampler -------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clk, mx = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= t <= t1 + 0.05:
+                sm.append(clk)
+                try:
+                    power.append(float(f[2]))
+                except ValueError:
+                    pass
+                for name, v in zip(self.NAMES, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            smax.append(mx)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- the reference's CPU strategy on a bounded sample (oracle port) ------------------------
+def cpu_reference_sample(n, n_spin, n_slabs, steps):
+    """J as a GEMV over the no-copy (ab)x(mu nu) view, K as permute-copy + GEMV per spin —
+    how the reference's @tensor lines execute on the CPU — on `n_slabs`
+    nu-slabs of the same synthetic tensor.  builds/s = 1 / (t_sample * n / n_slabs)."""
+    from oracle import synth
+    n_slabs = min(n_slabs, n)
+    eri = synth.hash_eri(n, nu_lo=0, nu_hi=n_slabs)                  # (n,n,n,S) F-ordered
+    da = synth.hash_symmetric_matrix(n, synth.SEED_DA)
+    db = synth.hash_symmetric_matrix(n, synth.SEED_DB)
+    dens = [da, db][:n_spin]
+    total = 2 * da if n_spin == 1 else da + db
+    n2 = n * n
+    times = []
+    for _ in range(steps + 1):
+        t0 = time.perf_counter()
+        m = eri.reshape(n2, n * n_slabs, order="F")
+        j = m.T @ total.reshape(n2, order="F")
+        out = []
+        for d in dens:                                               # one permuted copy per K line
+            p = np.asfortranarray(eri.transpose(2, 1, 0, 3)).reshape(n2, n * n_slabs, order="F")
+            out.append(j - p.T @ d.reshape(n2, order="F"))
+        times.append(time.perf_counter() - t0)
+    t = float(np.median(times[1:]))                                   # first pass = warm-up
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count()
+    return {"value": 1.0 / (t * n / n_slabs), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_slabs} of {n} nu-slabs of the same n_bf={n} hash tensor "
+                      f"({8 * n ** 3 * n_slabs / 1e9:.2f} GB), NumPy/OpenBLAS GEMV for J + "
+                      f"permute-copy+GEMV per spin for K, median of {steps} passes, scaled x{n}/{n_slabs}",
+            "sample_seconds": t}
+
+
+def run_reference(a, rank):
+    if rank != 0:
+        return
+    steps = max(1, min(a.steps, a.cpu_steps if a.cpu_steps else a.steps))
+    r = cpu_reference_sample(a.n_bas, a.n_spin, a.cpu_slabs, steps)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+            "n_gpus": a.gpus, "steps": steps, "warmup": 1,
+            "ms_per_step": 1000.0 / r["value"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "n_bas": a.n_bas, "n_spin": a.n_spin},
+            "cpu_baseline": r,
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---- ours ---------------------------------------------------------------------------------
+def run_ours(a, rank, local_rank, world):
+    import torch
+    import scf_b200
+    from scf_b200 import synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    comm_id = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [scf_b200.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm_id = box[0]
+
+    n, n_spin = a.n_bas, a.n_spin
+    n2 = n * n
+    builder = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synthetic.SEED_ERI, layout=a.layout,
+                                               device=local_rank, rank=rank, n_ranks=world)
+    if world > 1:
+        builder.comm_init(comm_id)
+    stream = torch.cuda.Stream()
+    builder.set_stream(stream.cuda_stream)
+
+    da = synthetic.hash_density(n, synthetic.SEED_DA)
+    db = synthetic.hash_density(n, synthetic.SEED_DB)
+    dens_h = np.asfortranarray(np.stack([da, db][:n_spin], axis=2))
+    total_h = np.asfortranarray(2 * da if n_spin == 1 else da + db)
+    # torch views of the column-major arrays: tensor[s, v, m] == density[m, v, s]
+    d_dens = torch.from_numpy(dens_h.T.copy()).cuda()
+    d_total = torch.from_numpy(total_h.T.copy()).cuda()
+    d_out = torch.zeros_like(d_dens)
+
+    def step():
+        builder.add_2e_term_device(d_out.data_ptr(), d_dens.data_ptr(), d_total.data_ptr(), n_spin)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = builder.launch_count
+    with torch.cuda.stream(stream):
+        for _ in range(a.warmup):
+            step()
+        barrier()
+        launches_w = builder.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_load0 = time.perf_counter()
+        e0.record()
+        for _ in range(a.steps):
+            step()
+        e1.record()
+        barrier()
+        t_load1 = time.perf_counter()
+        ms = e0.elapsed_time(e1)
+        launches = builder.launch_count - launches_w
+
+        # roofline pass: device time of the ERI-streaming kernel alone, per launch
+        stream_ms = []
+        for _ in range(a.steps):
+            step()
+            stream_ms.append(builder.last_build_ms()[0])
+        barrier()
+
+        # end to end through the public host-pointer API (pinned staging inside the library)
+        e2e_steps = a.e2e_steps or a.steps
+        out_h = np.zeros((n, n, n_spin), order="F")
+        for _ in range(min(3, a.warmup)):
+            builder.add_2e_term(out_h, dens_h, total_h)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            builder.add_2e_term(out_h, dens_h, total_h)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t_load2 = time.perf_counter()
+    clocks = sampler.stop(t_load0, t_load2) if sampler else None
+
+    if dist is not None:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = t.tolist()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        lo, hi = builder.shard_range
+        launch_bytes = 8.0 * n ** 3 * (hi - lo)             # algorithmic bytes of one stream launch
+        k_ms = float(np.mean(stream_ms))
+        achieved = launch_bytes / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "n_bas": n, "n_spin": n_spin,
+                       "layout": a.layout, "sharding": f"nu-slabs over {world} rank(s)",
+                       "l2_policy": "inputs (ERI shard) far larger than the 126 MB L2; no flush"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "jk_full_stream_kernel", "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": launch_bytes, "peak_source": peak_src,
+                         "kernel_share_of_step": k_ms / (ms / a.steps)},
+            "e2e": {"value": e2e_steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": 8 * n2 * (2 * n_spin + 1),
+                    "d2h_bytes_per_step": 8 * n2 * n_spin, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_sample(n, n_spin, a.cpu_slabs, a.cpu_steps)
+        print(json.dumps(line), flush=True)
+    builder.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit(f"--gpus {a.gpus} needs torchrun --nproc-per-node {a.gpus}")
+    run_ours(a, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

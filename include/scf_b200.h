@@ -1,0 +1,113 @@
+/* scf_b200.h — C ABI of libscf_b200.so: the B200-native Fock-build path that sits
+ * behind SelfConsistentField.jl's `TwoElectronBuilder` / `add_2e_term!` boundary.
+ *
+ * Conventions
+ *   - All matrices/tensors are dense, fp64, COLUMN-MAJOR (Julia layout):
+ *       eri[a,b,c,d]   at  a + n*b + n^2*c + n^3*d          (n = n_bas)
+ *       density[m,v,s] at  m + n*v + n^2*s                   (s = spin block)
+ *   - Every function returns an int status: 0 = ok, negative = error class below.
+ *     `scfb_last_error(h)` gives the message.  Nothing throws or aborts across the ABI.
+ *   - Host entry points are synchronous: outputs are valid on return.
+ *   - A handle is driven by ONE caller thread at a time (not re-entrant).
+ *   - One handle owns the ERI shard of ONE GPU.  Multi-GPU = one process (or thread)
+ *     per GPU, each with its own handle created with (rank, n_ranks); rank g owns the
+ *     contiguous nu-slabs (slowest ERI index) `scfb_shard_range` reports.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   src/types/ScfProblem.jl:2-9                 abstract TwoElectronBuilder + add_2e_term!
+ *   src/algorithms/JKBuilderFromTensor.jl:7-9   ERI storage           -> scfb_create / scfb_eri_*
+ *   src/algorithms/JKBuilderFromTensor.jl:22-51 add_2e_term!          -> scfb_fock_jk
+ *   src/parts/compute_fock_matrix.jl:8-71       Fock assembly/energies-> scfb_fock_assemble
+ *   src/parts/compute_pulay_error.jl:1-25       S D F - F D S         -> scfb_pulay_error
+ *   src/parts/compute_orbitals.jl:4-19          eigen(F, S)           -> scfb_sygvd
+ *   src/parts/compute_density.jl:4-35           C_occ C_occ'          -> scfb_density
+ *   src/algorithms/cDIIS.jl:123-127             B row tr(e1' ej)      -> scfb_diis_push / _row
+ *   src/parts/diis.jl:42-55                     F <- sum c_i F_i      -> scfb_diis_extrapolate
+ *   examples/HartreeFock.jl:88-95               J/K energy split      -> scfb_jk_energies
+ */
+#ifndef SCF_B200_H
+#define SCF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCFB_OK 0
+#define SCFB_ERR_ARG (-1)      /* bad argument / shape / precondition            */
+#define SCFB_ERR_CUDA (-2)     /* CUDA runtime error (incl. no device)           */
+#define SCFB_ERR_CUSOLVER (-3) /* cuSOLVER / cuBLAS failure                      */
+#define SCFB_ERR_NCCL (-4)     /* NCCL failure or libnccl not loadable           */
+#define SCFB_ERR_OOM (-5)      /* device allocation failed                       */
+#define SCFB_ERR_STATE (-6)    /* call sequence error (e.g. ERI not loaded yet)  */
+
+#define SCFB_LAYOUT_FULL 0    /* n^4 doubles, Julia order                                   */
+#define SCFB_LAYOUT_PACKED8 1 /* P(P+1)/2 doubles, P=n(n+1)/2, 8-fold-symmetric tensors only */
+
+#define SCFB_ERI_HASH 0  /* dense splitmix64 family (DESIGN.md "synthetic inputs")  */
+#define SCFB_ERI_CHAIN 1 /* soft-Coulomb dimerised chain (physical, SCF converges) */
+
+typedef struct scfb_handle_s* scfb_handle_t;
+
+/* ---- lifecycle --------------------------------------------------------------------- */
+int scfb_version(void);
+/* Creates a builder for an n_bas^4 ERI on CUDA device `device`.  (rank, n_ranks) select
+ * the nu-slab shard this handle owns; use (0, 1) for a single GPU.  Allocates the shard. */
+int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank, int n_ranks);
+int scfb_destroy(scfb_handle_t h); /* idempotent on NULL */
+const char* scfb_last_error(scfb_handle_t h); /* h may be NULL: last error of this thread */
+int scfb_sync(scfb_handle_t h);
+/* Run the handle's work on the caller's CUDA stream (e.g. torch's current stream). */
+int scfb_set_stream(scfb_handle_t h, void* cuda_stream);
+
+/* ---- ERI storage (JKBuilderFromTensor.jl:7-9) -------------------------------------- */
+int scfb_shard_range(scfb_handle_t h, int* nu_lo, int* nu_hi);
+int scfb_eri_bytes(scfb_handle_t h, uint64_t* bytes);
+/* `host_eri` is the FULL n^4 tensor; the handle copies (full layout) or packs (packed8,
+ * lower-triangle representatives) what it owns. */
+int scfb_eri_upload(scfb_handle_t h, const double* host_eri);
+/* Chunked variant, full layout: `host_slabs` holds nu_count consecutive nu-slabs starting
+ * at global slab nu_first; slabs outside the shard are skipped. */
+int scfb_eri_upload_slabs(scfb_handle_t h, const double* host_slabs, int nu_first, int nu_count);
+/* Declare the shard complete after a sequence of partial scfb_eri_upload_slabs calls. */
+int scfb_eri_mark_ready(scfb_handle_t h);
+/* Fill the shard on the device from a closed-form synthetic family.  `aux` is family
+ * specific: HASH ignores it; CHAIN expects 2*n doubles: x[n] then ... see DESIGN.md. */
+int scfb_eri_generate(scfb_handle_t h, int family, uint64_t seed, const double* aux);
+/* Copy the shard back (full layout only; debugging / parity at small n). */
+int scfb_eri_download(scfb_handle_t h, double* host_shard);
+
+/* ---- the hot path (JKBuilderFromTensor.jl:22-51) ----------------------------------- */
+/* out[:,:,s] += J[total_density] - K[density[:,:,s]],  s < n_spin in {1,2}.
+ *   J[m,v] = sum_ab eri[a,b,m,v] * total_density[a,b]
+ *   K[m,v] = sum_ab eri[m,b,a,v] * density[a,b,s]
+ * Host pointers; `out` is read, accumulated into and written back.  With n_ranks > 1 and
+ * an initialised communicator the partial J/K are allreduced first, so every rank
+ * returns the full result. */
+int scfb_fock_jk(scfb_handle_t h, int n_spin, const double* density,
+                 const double* total_density, double* out);
+/* Same with DEVICE pointers, asynchronous on the handle's stream. */
+int scfb_fock_jk_dev(scfb_handle_t h, int n_spin, const double* d_density,
+                     const double* d_total_density, double* d_out);
+/* J (n*n) and K (n*n*n_spin) separately, overwritten, host pointers. */
+int scfb_jk_split(scfb_handle_t h, int n_spin, const double* density,
+                  const double* total_density, double* J, double* K);
+/* Device time of the last build on this handle, measured with CUDA events on the
+ * handle's stream: `stream_ms` = the ERI-streaming kernel alone, `total_ms` = all
+ * launches of the build (stream + reduce + collective + accumulate). */
+int scfb_last_build_ms(scfb_handle_t h, double* stream_ms, double* total_ms);
+/* Number of kernels this library launched on this handle since creation. */
+int scfb_launch_count(scfb_handle_t h, uint64_t* launches);
+
+/* ---- multi-GPU exchange (one process per GPU) ------------------------- */
+/* Rank 0 calls scfb_comm_unique_id and ships the 128 bytes to the other ranks by any
+ * means (torch.distributed / MPI / a file); every rank then calls scfb_comm_init. */
+int scfb_comm_unique_id(char* id128);
+int scfb_comm_init(scfb_handle_t h, const char* id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCF_B200_H */

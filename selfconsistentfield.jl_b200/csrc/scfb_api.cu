@@ -1,0 +1,286 @@
+// C-ABI entry points of libscf_b200.so (declared in include/scf_b200.h): lifecycle, ERI
+// storage and the host/device-pointer Fock-build calls.  No CPU fallback anywhere: every
+// compute entry point needs a CUDA device and fails with SCFB_ERR_CUDA otherwise.
+#include <new>
+
+#include "scfb_internal.h"
+
+thread_local char scfb_tls_err[512] = {0};
+
+namespace {
+
+constexpr int kVersion = 100;  // 0.1.0
+
+int check_handle(scfb_handle_s* h) {
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess)
+    return scfb_fail(h, SCFB_ERR_CUDA, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e));
+  return SCFB_OK;
+}
+
+// stage the caller's host arrays into pinned memory and push them with one H2D copy
+// staging layout (host and device): [density 2n^2 | total n^2 | out 2n^2]
+int stage_inputs(scfb_handle_s* h, int n_spin, const double* density, const double* total,
+                 const double* out) {
+  const size_t n2 = (size_t)h->n * h->n;
+  std::memcpy(h->h_stage, density, n2 * n_spin * sizeof(double));
+  std::memcpy(h->h_stage + 2 * n2, total, n2 * sizeof(double));
+  size_t count = 3 * n2;
+  if (out) {
+    std::memcpy(h->h_stage + 3 * n2, out, n2 * n_spin * sizeof(double));
+    count = 3 * n2 + n2 * n_spin;
+  }
+  SCFB_CUDA(h, cudaMemcpyAsync(h->d_density, h->h_stage, count * sizeof(double),
+                               cudaMemcpyHostToDevice, h->stream));
+  return SCFB_OK;
+}
+
+int check_build_args(scfb_handle_s* h, int n_spin, const void* a, const void* b, const void* c) {
+  SCFB_REQUIRE(h, n_spin == 1 || n_spin == 2, "n_spin must be 1 or 2 (got %d)", n_spin);
+  SCFB_REQUIRE(h, a && b && c, "null array pointer");
+  if (!h->eri_ready) return scfb_fail(h, SCFB_ERR_STATE, "ERI not loaded: call scfb_eri_upload/_generate first");
+  return SCFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int scfb_version(void) { return kVersion; }
+
+const char* scfb_last_error(scfb_handle_t h) { return h ? h->err : scfb_tls_err; }
+
+int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank, int n_ranks) {
+  if (!out) return scfb_fail(nullptr, SCFB_ERR_ARG, "null output pointer");
+  *out = nullptr;
+  SCFB_REQUIRE(nullptr, n_bas >= 1, "n_bas must be >= 1 (got %d)", n_bas);
+  SCFB_REQUIRE(nullptr, layout == SCFB_LAYOUT_FULL || layout == SCFB_LAYOUT_PACKED8,
+               "unknown layout %d", layout);
+  SCFB_REQUIRE(nullptr, n_ranks >= 1 && rank >= 0 && rank < n_ranks, "bad rank %d of %d", rank,
+               n_ranks);
+  SCFB_REQUIRE(nullptr, (n_bas % 2 == 0 && n_bas <= 512) || (n_bas % 2 == 1 && n_bas <= 255),
+               "n_bas=%d unsupported: even n <= 512 or odd n <= 255", n_bas);
+  SCFB_REQUIRE(nullptr, layout == SCFB_LAYOUT_FULL, "packed8 layout not built yet");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return scfb_fail(nullptr, SCFB_ERR_CUDA, "no CUDA device: %s (there is no CPU fallback)",
+                     cudaGetErrorString(e));
+  SCFB_REQUIRE(nullptr, device >= 0 && device < n_dev, "device %d out of range (%d visible)",
+               device, n_dev);
+
+  scfb_handle_s* h = new (std::nothrow) scfb_handle_s();
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_OOM, "host allocation failed");
+  h->n = n_bas;
+  h->layout = layout;
+  h->device = device;
+  h->rank = rank;
+  h->n_ranks = n_ranks;
+  scfb_split_range(n_bas, rank, n_ranks, &h->nu_lo, &h->nu_hi);
+  const uint64_t n = n_bas, n2 = n * n;
+  h->eri_elems = n2 * n * (uint64_t)(h->nu_hi - h->nu_lo);
+  h->kpart_elems = scfb_kpart_elems_full(n_bas, h->nu_hi - h->nu_lo);
+
+#define CREATE_CUDA(call)                                                                   \
+  do {                                                                                      \
+    cudaError_t e2_ = (call);                                                               \
+    if (e2_ != cudaSuccess) {                                                               \
+      int rc_ = scfb_fail(nullptr, e2_ == cudaErrorMemoryAllocation ? SCFB_ERR_OOM : SCFB_ERR_CUDA, \
+                          "scfb_create: %s -> %s", #call, cudaGetErrorString(e2_));         \
+      scfb_destroy(h);                                                                      \
+      return rc_;                                                                           \
+    }                                                                                       \
+  } while (0)
+
+  CREATE_CUDA(cudaSetDevice(device));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& ev : h->ev) CREATE_CUDA(cudaEventCreate(&ev));
+  h->timed = true;
+  if (h->eri_elems) CREATE_CUDA(cudaMalloc(&h->eri, h->eri_elems * sizeof(double)));
+  CREATE_CUDA(cudaMalloc(&h->d_density, 5 * n2 * sizeof(double)));
+  h->d_total = h->d_density + 2 * n2;
+  h->d_out = h->d_density + 3 * n2;
+  CREATE_CUDA(cudaMalloc(&h->jk, 3 * n2 * sizeof(double)));
+  CREATE_CUDA(cudaMemsetAsync(h->jk, 0, 3 * n2 * sizeof(double), h->stream));
+  if (h->kpart_elems) CREATE_CUDA(cudaMalloc(&h->kpart, h->kpart_elems * sizeof(double)));
+  CREATE_CUDA(cudaMallocHost(&h->h_stage, 5 * n2 * sizeof(double)));
+  CREATE_CUDA(cudaStreamSynchronize(h->stream));
+#undef CREATE_CUDA
+  *out = h;
+  return SCFB_OK;
+}
+
+int scfb_destroy(scfb_handle_t h) {
+  if (!h) return SCFB_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  scfb_comm_destroy(h);
+  cudaFree(h->eri);
+  cudaFree(h->d_density);
+  cudaFree(h->jk);
+  cudaFree(h->kpart);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  for (auto& ev : h->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return SCFB_OK;
+}
+
+int scfb_sync(scfb_handle_t h) {
+  if (int rc = check_handle(h)) return rc;
+  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SCFB_OK;
+}
+
+int scfb_set_stream(scfb_handle_t h, void* cuda_stream) {
+  if (int rc = check_handle(h)) return rc;
+  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  h->stream = static_cast<cudaStream_t>(cuda_stream);
+  h->own_stream = false;
+  return SCFB_OK;
+}
+
+int scfb_shard_range(scfb_handle_t h, int* nu_lo, int* nu_hi) {
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  if (nu_lo) *nu_lo = h->nu_lo;
+  if (nu_hi) *nu_hi = h->nu_hi;
+  return SCFB_OK;
+}
+
+int scfb_eri_bytes(scfb_handle_t h, uint64_t* bytes) {
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  if (bytes) *bytes = h->eri_elems * sizeof(double);
+  return SCFB_OK;
+}
+
+int scfb_eri_upload_slabs(scfb_handle_t h, const double* host_slabs, int nu_first, int nu_count) {
+  if (int rc = check_handle(h)) return rc;
+  SCFB_REQUIRE(h, host_slabs, "null host pointer");
+  SCFB_REQUIRE(h, nu_first >= 0 && nu_count >= 0 && nu_first + nu_count <= h->n,
+               "slab range [%d, %d) outside [0, %d)", nu_first, nu_first + nu_count, h->n);
+  const int lo = nu_first > h->nu_lo ? nu_first : h->nu_lo;
+  const int hi = nu_first + nu_count < h->nu_hi ? nu_first + nu_count : h->nu_hi;
+  if (hi > lo) {
+    const uint64_t n3 = (uint64_t)h->n * h->n * h->n;
+    SCFB_CUDA(h, cudaMemcpyAsync(h->eri + (uint64_t)(lo - h->nu_lo) * n3,
+                                 host_slabs + (uint64_t)(lo - nu_first) * n3,
+                                 (uint64_t)(hi - lo) * n3 * sizeof(double), cudaMemcpyHostToDevice,
+                                 h->stream));
+    SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  if (lo <= h->nu_lo && hi >= h->nu_hi) h->eri_ready = true;  // whole shard arrived in one call
+  return SCFB_OK;
+}
+
+int scfb_eri_upload(scfb_handle_t h, const double* host_eri) {
+  int rc = scfb_eri_upload_slabs(h, host_eri, 0, h ? h->n : 0);
+  if (rc == SCFB_OK) h->eri_ready = true;
+  return rc;
+}
+
+int scfb_eri_mark_ready(scfb_handle_t h) {  // after a sequence of partial slab uploads
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  h->eri_ready = true;
+  return SCFB_OK;
+}
+
+int scfb_eri_generate(scfb_handle_t h, int family, uint64_t seed, const double* aux) {
+  if (int rc = check_handle(h)) return rc;
+  SCFB_REQUIRE(h, family == SCFB_ERI_HASH || family == SCFB_ERI_CHAIN, "unknown family %d", family);
+  double* d_aux = nullptr;
+  if (family == SCFB_ERI_CHAIN) {
+    SCFB_REQUIRE(h, aux, "CHAIN family needs aux = [soft, x[n], S[n*n]]");
+    const size_t cnt = 1 + (size_t)h->n + (size_t)h->n * h->n;
+    SCFB_CUDA(h, cudaMalloc(&d_aux, cnt * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d_aux, aux, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) {
+      cudaFree(d_aux);
+      return scfb_fail(h, SCFB_ERR_CUDA, "aux upload: %s", cudaGetErrorString(e));
+    }
+  }
+  int rc = scfb_launch_generate_full(h, family, seed, d_aux);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (d_aux) cudaFree(d_aux);
+  if (rc) return rc;
+  if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "generate: %s", cudaGetErrorString(e));
+  h->eri_ready = true;
+  return SCFB_OK;
+}
+
+int scfb_eri_download(scfb_handle_t h, double* host_shard) {
+  if (int rc = check_handle(h)) return rc;
+  SCFB_REQUIRE(h, host_shard, "null host pointer");
+  SCFB_CUDA(h, cudaMemcpyAsync(host_shard, h->eri, h->eri_elems * sizeof(double),
+                               cudaMemcpyDeviceToHost, h->stream));
+  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SCFB_OK;
+}
+
+int scfb_fock_jk_dev(scfb_handle_t h, int n_spin, const double* d_density,
+                     const double* d_total_density, double* d_out) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_build_args(h, n_spin, d_density, d_total_density, d_out)) return rc;
+  if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+  if (int rc = scfb_launch_jk_full(h, n_spin, d_density, d_total_density)) return rc;
+  if (h->n_ranks > 1 && h->nccl_comm)
+    if (int rc = scfb_comm_allreduce_jk(h, n_spin)) return rc;
+  if (int rc = scfb_launch_accumulate(h, n_spin, d_out)) return rc;
+  if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+  return SCFB_OK;
+}
+
+int scfb_fock_jk(scfb_handle_t h, int n_spin, const double* density, const double* total_density,
+                 double* out) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_build_args(h, n_spin, density, total_density, out)) return rc;
+  if (int rc = stage_inputs(h, n_spin, density, total_density, out)) return rc;
+  if (int rc = scfb_fock_jk_dev(h, n_spin, h->d_density, h->d_total, h->d_out)) return rc;
+  const size_t n2 = (size_t)h->n * h->n;
+  SCFB_CUDA(h, cudaMemcpyAsync(h->h_stage + 3 * n2, h->d_out, n2 * n_spin * sizeof(double),
+                               cudaMemcpyDeviceToHost, h->stream));
+  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::memcpy(out, h->h_stage + 3 * n2, n2 * n_spin * sizeof(double));
+  return SCFB_OK;
+}
+
+int scfb_jk_split(scfb_handle_t h, int n_spin, const double* density, const double* total_density,
+                  double* J, double* K) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_build_args(h, n_spin, density, total_density, J)) return rc;
+  SCFB_REQUIRE(h, K, "null K pointer");
+  if (int rc = stage_inputs(h, n_spin, density, total_density, nullptr)) return rc;
+  if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+  if (int rc = scfb_launch_jk_full(h, n_spin, h->d_density, h->d_total)) return rc;
+  if (h->n_ranks > 1 && h->nccl_comm)
+    if (int rc = scfb_comm_allreduce_jk(h, n_spin)) return rc;
+  if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+  const size_t n2 = (size_t)h->n * h->n;
+  SCFB_CUDA(h, cudaMemcpyAsync(h->h_stage, h->jk, (1 + n_spin) * n2 * sizeof(double),
+                               cudaMemcpyDeviceToHost, h->stream));
+  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::memcpy(J, h->h_stage, n2 * sizeof(double));
+  std::memcpy(K, h->h_stage + n2, n2 * n_spin * sizeof(double));
+  return SCFB_OK;
+}
+
+int scfb_last_build_ms(scfb_handle_t h, double* stream_ms, double* total_ms) {
+  if (int rc = check_handle(h)) return rc;
+  SCFB_CUDA(h, cudaEventSynchronize(h->ev[2]));
+  float a = 0.f, b = 0.f;
+  SCFB_CUDA(h, cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+  SCFB_CUDA(h, cudaEventElapsedTime(&b, h->ev[0], h->ev[2]));
+  if (stream_ms) *stream_ms = a;
+  if (total_ms) *total_ms = b;
+  return SCFB_OK;
+}
+
+int scfb_launch_count(scfb_handle_t h, uint64_t* launches) {
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  if (launches) *launches = h->launches;
+  return SCFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// Internal state of a libscf_b200 handle.  Not part of the ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/scf_b200.h"
+
+struct scfb_handle_s {
+  int n = 0;             // n_bas
+  int layout = SCFB_LAYOUT_FULL;
+  int device = 0;
+  int rank = 0, n_ranks = 1;
+  int nu_lo = 0, nu_hi = 0;  // owned nu-slabs (full layout) — [lo, hi)
+  // packed layout: owned rows [row_lo, row_hi) of the lower-triangular P x P pair matrix
+  int64_t row_lo = 0, row_hi = 0;
+
+  double* eri = nullptr;  // device shard
+  uint64_t eri_elems = 0;
+  bool eri_ready = false;
+
+  // device scratch
+  double* d_density = nullptr;  // n*n*2   (host-pointer API staging)
+  double* d_total = nullptr;    // n*n
+  double* d_out = nullptr;      // n*n*2
+  double* jk = nullptr;         // [J | K_0 | K_1], 3*n*n, zero outside owned columns
+  double* kpart = nullptr;      // per-(nu, c-chunk) partial K rows
+  uint64_t kpart_elems = 0;
+  double* h_stage = nullptr;    // pinned host staging, 5*n*n
+
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // build start, stream end, build end
+  bool timed = false;
+  uint64_t launches = 0;
+
+  void* nccl_comm = nullptr;  // ncclComm_t when n_ranks > 1 and initialised
+
+  char err[512] = {0};
+};
+
+// thread-local message for calls that fail before a handle exists
+extern thread_local char scfb_tls_err[512];
+
+inline int scfb_fail(scfb_handle_s* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  std::snprintf(scfb_tls_err, sizeof scfb_tls_err, "%s", buf);
+  if (h) std::snprintf(h->err, sizeof h->err, "%s", buf);
+  return code;
+}
+
+#define SCFB_CUDA(h, call)                                                              \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return scfb_fail((h), e_ == cudaErrorMemoryAllocation ? SCFB_ERR_OOM : SCFB_ERR_CUDA, \
+                       "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define SCFB_REQUIRE(h, cond, ...) \
+  do {                             \
+    if (!(cond)) return scfb_fail((h), SCFB_ERR_ARG, __VA_ARGS__); \
+  } while (0)
+
+// contiguous nu-slab ownership; ragged remainder goes to the first ranks
+inline void scfb_split_range(int n, int rank, int n_ranks, int* lo, int* hi) {
+  int base = n / n_ranks, rem = n % n_ranks;
+  *lo = rank * base + (rank < rem ? rank : rem);
+  *hi = *lo + base + (rank < rem ? 1 : 0);
+}
+
+// ---- kernels / launchers implemented in the .cu files --------------------------------
+// jk_full.cu
+int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
+                        const double* d_total);            // fills h->jk for owned columns
+int scfb_launch_accumulate(scfb_handle_s* h, int n_spin, double* d_out);  // out += J - K_s
+uint64_t scfb_kpart_elems_full(int n, int n_slabs);
+// eri_gen.cu
+int scfb_launch_generate_full(scfb_handle_s* h, int family, uint64_t seed, const double* d_aux);
+// comm.cu
+int scfb_comm_allreduce_jk(scfb_handle_s* h, int n_spin);
+int scfb_comm_destroy(scfb_handle_s* h);

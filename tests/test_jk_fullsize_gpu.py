@@ -1,0 +1,77 @@
+"""Full-size (BASELINE.json config 3: UHF n_bf=256, 34 GB full fp64 ERI) checks through the
+C ABI.  The oracle cannot hold this tensor, so parity is established by exact known answers
+(the HASH family is O(1) per element) and size-independent properties."""
+import numpy as np
+import pytest
+
+import scf_b200
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+N = 256
+
+
+@pytest.fixture(scope="module")
+def builder():
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs 40 GB of free HBM")
+    b = scf_b200.JKBuilderCUDA.synthetic(N, "hash", synth.SEED_ERI)
+    assert b.eri_bytes == 8 * N ** 4
+    yield b
+    b.close()
+
+
+def unit(n, i, j):
+    m = np.zeros((n, n))
+    m[i, j] = 1.0
+    return m
+
+
+def test_unit_density_known_answers_are_bit_exact(builder):
+    """D = e_a e_b' picks single tensor elements: J[c,v] = eri[a,b,c,v], K[m,v] = eri[m,b,a,v]
+    (JKBuilderFromTensor.jl:37) — compared bit for bit with the host hash."""
+    idx = np.arange(N)
+    for (a0, b0), (a1, b1), (a2, b2) in [((3, 250), (17, 5), (255, 255)), ((0, 0), (128, 127), (64, 200))]:
+        total = unit(N, a0, b0)
+        density = np.stack([unit(N, a1, b1), unit(N, a2, b2)], axis=2)
+        j, k = builder.jk(density, total)
+        assert np.array_equal(j, synth.hash_eri_elements(a0, b0, idx[:, None], idx[None, :]))
+        assert np.array_equal(k[:, :, 0], synth.hash_eri_elements(idx[:, None], b1, a1, idx[None, :]))
+        assert np.array_equal(k[:, :, 1], synth.hash_eri_elements(idx[:, None], b2, a2, idx[None, :]))
+
+
+def test_reciprocity_symmetry_linearity(builder):
+    da = synth.hash_symmetric_matrix(N, synth.SEED_DA)
+    db = synth.hash_symmetric_matrix(N, synth.SEED_DB)
+    dens = np.stack([da, db], axis=2)
+    j1, k1 = builder.jk(dens, da + db)
+    # symmetric D, 8-fold symmetric tensor -> symmetric J, K
+    for m in (j1, k1[:, :, 0], k1[:, :, 1]):
+        assert np.abs(m - m.T).max() < 1e-12 * np.abs(m).max()
+    # reciprocity: <W, J[D]> = <D, J[W]>, <W, K[D]> = <D, K[W]>
+    w = synth.hash_symmetric_matrix(N, 99)
+    jw, kw = builder.jk(np.stack([w, w], axis=2), w)
+    scale = np.abs(j1).max() * np.abs(w).sum()
+    assert abs(np.sum(w * j1) - np.sum((da + db) * jw)) < 1e-12 * scale
+    assert abs(np.sum(w * k1[:, :, 0]) - np.sum(da * kw[:, :, 0])) < 1e-12 * scale
+    # linearity in D
+    j2, k2 = builder.jk(np.stack([da + 0.5 * w, db - 2 * w], axis=2), da + db + 3 * w)
+    assert np.abs(j2 - (j1 + 3 * jw)).max() < 1e-12 * np.abs(j2).max()
+    assert np.abs(k2[:, :, 0] - (k1[:, :, 0] + 0.5 * kw[:, :, 0])).max() < 1e-12 * np.abs(k2).max()
+    assert np.abs(k2[:, :, 1] - (k1[:, :, 1] - 2 * kw[:, :, 1])).max() < 1e-12 * np.abs(k2).max()
+
+
+def test_rhf_and_uhf_share_one_pass_results(builder):
+    """RHF call (n_spin=1, Dtot=2Da) and UHF call with Da=Db must agree exactly."""
+    da = synth.hash_symmetric_matrix(N, synth.SEED_DA)
+    j1, k1 = builder.jk(da[:, :, None], 2 * da)
+    j2, k2 = builder.jk(np.stack([da, da], axis=2), 2 * da)
+    assert np.array_equal(j1, j2)
+    assert np.array_equal(k1[:, :, 0], k2[:, :, 0]) and np.array_equal(k2[:, :, 0], k2[:, :, 1])
+    out = np.zeros((N, N, 1), order="F")
+    builder.add_2e_term(out, da[:, :, None], 2 * da)
+    assert np.array_equal(out[:, :, 0], j1 - k1[:, :, 0])
+    j3, k3 = builder.jk(da[:, :, None], 2 * da)
+    assert np.array_equal(j1, j3) and np.array_equal(k1, k3)      # deterministic

@@ -1,0 +1,214 @@
+"""GPU parity tests proper: the CUDA J/K path, called through the C ABI
+(`JKBuilderCUDA` = ctypes over libscf_b200.so), against the CPU oracle on the same inputs.
+
+Tolerance (north star): J and K within 1e-12 relative of the reference contraction,
+metric max|Δ| / max|J or K| against the extended-precision oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import scf_b200
+from oracle import scf_oracle as o
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def rel_err(x, ref):
+    return np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+def check_jk(builder, eri, density, total, exact=True):
+    j, k = builder.jk(density, total)
+    if exact:
+        jr, kr = o.jk_exact(eri, density, total)
+    else:
+        g = o.add_2e_term_blas  # noqa: F841  (large n: fp64 BLAS evaluation)
+        jr = o.coulomb(eri, total)
+        kr = np.stack([o.exchange(eri, density[:, :, s]) for s in range(density.shape[2])], axis=2)
+    assert rel_err(j, jr) < RTOL
+    for s in range(density.shape[2]):
+        assert rel_err(k[:, :, s], kr[:, :, s]) < RTOL
+    return j, k
+
+
+# ---- the reference's own fixtures ------------------------------------------------------
+@pytest.mark.parametrize("name", ["rhf_be_321g", "uhf_be_321g", "rohf_c_321g", "uhf_c_321g"])
+def test_golden_fixture_first_fock_build(golden_dir, name):
+    case = json.load(open(os.path.join(golden_dir, "golden_energies.json")))[name]
+    system, integrals = o.load_integral_npz(os.path.join(golden_dir, case["file"] + ".npz"))
+    problem = o.assemble_hf_problem(system, integrals, restricted=case["restricted"])
+    density = o.compute_guess_hcore(problem)
+    if (not problem.restricted) and problem.n_elec[0] == problem.n_elec[1]:
+        o.break_spin_symmetry(density)     # makes the beta density non-trivially different
+    n_spin = density.shape[2]
+    total = 2 * density[:, :, 0] if n_spin == 1 else density[:, :, 0] + density[:, :, 1]
+    eri = integrals["electron_repulsion_bbbb"]
+    b = scf_b200.JKBuilderCUDA.from_tensor(eri)
+    check_jk(b, eri, density, total)
+    # add_2e_term! accumulates into a pre-filled `out` (JKBuilderFromTensor.jl:39,48-49)
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal((9, 9, n_spin))
+    out = np.asfortranarray(base.copy())
+    ret = b.add_2e_term(out, density, total)
+    assert ret is out
+    ref = o.add_2e_term_exact(base.copy(), eri, density, total)
+    assert rel_err(out, ref) < RTOL
+    # C-ordered `out` takes the copy-in/copy-out path and must give the same answer
+    out_c = np.ascontiguousarray(base.copy())
+    b.add_2e_term(out_c, density, total)
+    assert np.array_equal(out_c, out)
+    b.close()
+
+
+def test_golden_energy_through_cuda_builder(golden_dir):
+    """Full SCF with the oracle's loop but the CUDA builder plugged in at the
+    add_2e_term! boundary -> the reference's golden RHF/UHF energies."""
+    cases = json.load(open(os.path.join(golden_dir, "golden_energies.json")))
+    for name in ("rhf_be_321g", "uhf_c_321g"):
+        case = cases[name]
+        system, integrals = o.load_integral_npz(os.path.join(golden_dir, case["file"] + ".npz"))
+        integrals["jk_builder_bb"] = scf_b200.JKBuilderCUDA.from_tensor(
+            integrals["electron_repulsion_bbbb"])
+        problem = o.assemble_hf_problem(system, integrals, restricted=case["restricted"])
+        guess = o.compute_guess_hcore(problem)
+        res = o.run_scf(problem, guess)
+        assert res["converged"]
+        assert res["energies"]["total"] == pytest.approx(case["e_total"], rel=1e-9, abs=0)
+        assert abs(res["energies_newest"]["total"] - case["e_total"]) < 1e-10
+
+
+# ---- arbitrary tensors / densities: the literal index patterns ---------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 9, 15, 16, 17, 24, 33, 40])
+@pytest.mark.parametrize("n_spin", [1, 2])
+def test_random_unsymmetric_inputs(n, n_spin):
+    rng = np.random.default_rng(1000 * n + n_spin)
+    eri = rng.standard_normal((n, n, n, n))          # no permutational symmetry
+    density = rng.standard_normal((n, n, n_spin))    # not symmetric
+    total = rng.standard_normal((n, n))              # caller-supplied, unrelated to density
+    b = scf_b200.JKBuilderCUDA.from_tensor(eri)
+    check_jk(b, eri, density, total)
+    b.close()
+
+
+def test_hypothesis_small_cases():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(n=st.integers(2, 24), n_spin=st.sampled_from([1, 2]), seed=st.integers(0, 2 ** 31))
+    def run(n, n_spin, seed):
+        rng = np.random.default_rng(seed)
+        eri = rng.uniform(-1, 1, (n, n, n, n))
+        density = rng.uniform(-1, 1, (n, n, n_spin))
+        total = rng.uniform(-1, 1, (n, n))
+        b = scf_b200.JKBuilderCUDA.from_tensor(eri)
+        try:
+            check_jk(b, eri, density, total)
+        finally:
+            b.close()
+
+    run()
+
+
+# ---- device generators == host twins, bit for bit ----------------------------------------
+@pytest.mark.parametrize("n", [6, 17, 32])
+def test_hash_generator_matches_host_twin(n):
+    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI)
+    assert np.array_equal(b.eri_shard(), synth.hash_eri(n))
+    b.close()
+
+
+@pytest.mark.parametrize("n", [8, 18])
+def test_chain_generator_matches_host_twin(n):
+    model = scf_b200.synthetic.ChainModel(n)
+    x, s, t, v, enn = synth.chain_matrices(n)
+    assert np.array_equal(model.overlap, s) and np.array_equal(model.kinetic, t)
+    assert np.allclose(model.nuclear_attraction, v, rtol=0, atol=1e-13)
+    assert abs(model.nuclear_repulsion - enn) < 1e-12
+    b = scf_b200.JKBuilderCUDA.synthetic(n, "chain", 0, aux=model.aux)
+    dev, host = b.eri_shard(), synth.chain_eri(n)
+    assert np.array_equal(dev, host)
+    b.close()
+
+
+# ---- medium sizes against the fp64 oracle ------------------------------------------------
+@pytest.mark.parametrize("n,n_spin", [(64, 1), (64, 2), (96, 2), (100, 1), (127, 2)])
+def test_hash_family_medium(n, n_spin):
+    eri = synth.hash_eri(n)
+    da = synth.hash_symmetric_matrix(n, synth.SEED_DA)
+    db = synth.hash_symmetric_matrix(n, synth.SEED_DB)
+    density = np.stack([da, db][:n_spin], axis=2)
+    total = 2 * da if n_spin == 1 else da + db
+    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI)
+    j, k = b.jk(density, total)
+    n2 = n * n
+    m = eri.reshape(n2, n2, order="F")
+    jr = (m.T @ total.reshape(n2, order="F")).reshape(n, n, order="F")
+    assert rel_err(j, jr) < RTOL
+    for s in range(n_spin):
+        kr = np.einsum("mban,ab->mn", eri, density[:, :, s], optimize=True)
+        assert rel_err(k[:, :, s], kr) < RTOL
+    # 8-fold symmetric tensor + symmetric D  =>  J and K symmetric
+    assert rel_err(j, j.T) < RTOL and rel_err(k[:, :, 0], k[:, :, 0].T) < RTOL
+    b.close()
+
+
+# ---- sharding: sum of per-rank partials == unsharded (no NCCL needed) --------------------
+@pytest.mark.parametrize("n,n_ranks", [(12, 2), (10, 4), (9, 8), (5, 8)])
+def test_shard_partials_sum_to_full(n, n_ranks):
+    rng = np.random.default_rng(n * 10 + n_ranks)
+    eri = rng.standard_normal((n, n, n, n))
+    density = rng.standard_normal((n, n, 2))
+    total = density[:, :, 0] + density[:, :, 1]
+    full = scf_b200.JKBuilderCUDA.from_tensor(eri)
+    jf, kf = full.jk(density, total)
+    js, ks = np.zeros_like(jf), np.zeros_like(kf)
+    covered = []
+    for g in range(n_ranks):
+        part = scf_b200.JKBuilderCUDA.from_tensor(eri, rank=g, n_ranks=n_ranks)
+        lo, hi = part.shard_range
+        assert (lo, hi) == o.shard_range(n, g, n_ranks)
+        covered.append((lo, hi))
+        j, k = part.jk(density, total)
+        mask = np.ones(n, bool)
+        mask[lo:hi] = False
+        assert not j[:, mask].any() and not k[:, mask, :].any()   # zero outside owned columns
+        js += j
+        ks += k
+        part.close()
+    assert np.array_equal(js, jf) and np.array_equal(ks, kf)     # columns are disjoint: exact
+    full.close()
+
+
+# ---- determinism, error behaviour -------------------------------------------------------
+def test_bitwise_reproducible():
+    n = 48
+    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", 7)
+    d = synth.hash_symmetric_matrix(n, 11)[:, :, None]
+    j1, k1 = b.jk(d, 2 * d[:, :, 0])
+    for _ in range(3):
+        j2, k2 = b.jk(d, 2 * d[:, :, 0])
+        assert np.array_equal(j1, j2) and np.array_equal(k1, k2)
+    b.close()
+
+
+def test_error_behaviour():
+    b = scf_b200.JKBuilderCUDA(6)
+    d = np.zeros((6, 6, 1))
+    with pytest.raises(scf_b200.ScfbError) as ei:      # ERI not uploaded yet
+        b.jk(d, d[:, :, 0])
+    assert ei.value.code == scf_b200.capi.ERR_STATE
+    b.close()
+    b = scf_b200.JKBuilderCUDA.synthetic(6, "hash", 1)
+    with pytest.raises(AssertionError):                 # JKBuilderFromTensor.jl:30-32
+        b.add_2e_term(np.zeros((6, 6, 3)), np.zeros((6, 6, 3)), np.zeros((6, 6)))
+    with pytest.raises(AssertionError):
+        b.add_2e_term(np.zeros((6, 6, 1)), np.zeros((6, 6, 1)), np.zeros((5, 5)))
+    with pytest.raises(AssertionError):
+        b.add_2e_term(np.zeros((6, 6, 2)), np.zeros((6, 6, 1)), np.zeros((6, 6)))
+    b.close()
+    with pytest.raises(scf_b200.ScfbError):
+        scf_b200.JKBuilderCUDA(6, device=99)
