@@ -49,7 +49,7 @@ int load_nccl(scfb_handle_s* h) {
 
 int scfb_comm_allreduce_jk(scfb_handle_s* h, int n_spin) {
   const size_t count = (size_t)(1 + n_spin) * h->n * h->n;
-  ncclResult_t r = g_nccl.AllReduce(h->jk, h->jk, count, ncclDouble, ncclSum,
+  ncclResult_t r = g_nccl.AllReduce(h->jk, h->jk_sum, count, ncclDouble, ncclSum,
                                     static_cast<ncclComm_t>(h->nccl_comm), h->stream);
   if (r != ncclSuccess)
     return scfb_fail(h, SCFB_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));

@@ -1,0 +1,607 @@
+// K4/K5 — the small dense steps that surround the Fock build in one SCF iteration, kept on
+// the device so that only scalars and <= 6x6 systems cross PCIe per iteration:
+//   Fock assembly + energies   /root/reference/src/parts/compute_fock_matrix.jl:8-58
+//   Pulay error S D F - F D S  /root/reference/src/parts/compute_pulay_error.jl:17-25
+//   orbitals  eigen(F, S)      /root/reference/src/parts/compute_orbitals.jl:4-19  (cuSOLVER Dsygvd)
+//   density   C_occ C_occ'     /root/reference/src/parts/compute_density.jl:4-35
+//   DIIS rows / extrapolation  /root/reference/src/algorithms/cDIIS.jl:123-127,
+//                              /root/reference/src/algorithms/EDIIS.jl:87,
+//                              /root/reference/src/parts/diis.jl:42-55
+// These are O(n^3) / O(n^2) — <1 % of a build's bytes — so cuBLAS GEMMs are used for the
+// products and tiny fixed-order (deterministic) reduction kernels for traces and dots.
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
+#include <vector>
+
+#include "scfb_internal.h"
+
+struct scfb_scf_state {
+  int n = 0, n_orb = 0, n_elec[2] = {0, 0};
+  int n_spin = 1;  // spin blocks of density / Fock (1 = RHF closed shell, 2 = UHF)
+  bool restricted = true;
+  double e0 = 0.0;
+  int cap = 5;  // n_diis_size
+
+  cublasHandle_t blas = nullptr;
+  cusolverDnHandle_t solver = nullptr;
+
+  double *S = nullptr, *H = nullptr;                       // n^2
+  double *F = nullptr, *Fnew = nullptr, *D = nullptr;      // 2 n^2 each
+  double *Dtot = nullptr, *G = nullptr, *E = nullptr;      // n^2, 2 n^2, 2 n^2
+  double *C = nullptr, *eps = nullptr;                     // 2 n^2, 2 n
+  double *T1 = nullptr, *T2 = nullptr, *Bw = nullptr;      // n^2 scratch
+  double *work = nullptr;
+  int lwork = 0;
+  int* dev_info = nullptr;
+  double* scal = nullptr;    // device scalars
+  double* h_scal = nullptr;  // pinned mirror
+  double* coef = nullptr;    // device copy of DIIS coefficients
+
+  // DIIS history: per spin, `cap` slots of (F, e, D); order[s] lists slot ids newest first
+  double *Fh = nullptr, *Eh = nullptr, *Dh = nullptr;  // [2][cap][n^2]
+  std::vector<int> order[2];
+  bool have_density = false, have_fock = false;
+};
+
+namespace {
+
+constexpr int kScal = 64;
+
+#define SCFB_BLAS(h, call)                                                                  \
+  do {                                                                                      \
+    cublasStatus_t s_ = (call);                                                             \
+    if (s_ != CUBLAS_STATUS_SUCCESS)                                                        \
+      return scfb_fail((h), SCFB_ERR_CUSOLVER, "%s:%d %s -> cublas status %d", __FILE__, __LINE__, \
+                       #call, (int)s_);                                                     \
+  } while (0)
+#define SCFB_SOLVER(h, call)                                                                \
+  do {                                                                                      \
+    cusolverStatus_t s_ = (call);                                                           \
+    if (s_ != CUSOLVER_STATUS_SUCCESS)                                                      \
+      return scfb_fail((h), SCFB_ERR_CUSOLVER, "%s:%d %s -> cusolver status %d", __FILE__,  \
+                       __LINE__, #call, (int)s_);                                           \
+  } while (0)
+
+// out[k] = sum_ij A_k[i,j] * B_k[j,i]  (= tr(A_k B_k)); one CTA per k, fixed-order tree.
+struct TracePair {
+  const double* a;
+  const double* b;
+  int transpose_b;  // 1: tr(A B) = sum A[i,j] B[j,i];  0: <A,B> = sum A[i,j] B[i,j]
+};
+constexpr int kMaxPairs = 16;
+struct TraceBatch {
+  TracePair p[kMaxPairs];
+};
+
+__global__ void __launch_bounds__(1024) trace_kernel(TraceBatch batch, int n, double* out) {
+  __shared__ double red[32];
+  const TracePair pr = batch.p[blockIdx.x];
+  const size_t n2 = (size_t)n * n;
+  double acc = 0.0;
+  for (size_t e = threadIdx.x; e < n2; e += blockDim.x) {
+    const size_t i = e % n, j = e / n;
+    const double bv = pr.transpose_b ? pr.b[j + i * n] : pr.b[e];
+    acc = fma(pr.a[e], bv, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) out[blockIdx.x] = v;
+  }
+}
+
+// EDIIS row entry: tr((F1 - Fj)(D1 - Dj)) = sum_ik (F1-Fj)[i,k] (D1-Dj)[k,i]
+struct EdiisBatch {
+  const double* f1;
+  const double* d1;
+  const double* fj[kMaxPairs];
+  const double* dj[kMaxPairs];
+};
+__global__ void __launch_bounds__(1024) ediis_row_kernel(EdiisBatch b, int n, double* out) {
+  __shared__ double red[32];
+  const double* fj = b.fj[blockIdx.x];
+  const double* dj = b.dj[blockIdx.x];
+  const size_t n2 = (size_t)n * n;
+  double acc = 0.0;
+  for (size_t e = threadIdx.x; e < n2; e += blockDim.x) {
+    const size_t i = e % n, k = e / n;
+    const size_t et = k + i * n;
+    acc = fma(b.f1[e] - fj[e], b.d1[et] - dj[et], acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) out[blockIdx.x] = v;
+  }
+}
+
+// Dtot = 2 Da (one spin block) or Da + Db; G = 0
+__global__ void prepare_build_kernel(const double* __restrict__ D, double* __restrict__ Dtot,
+                                     double* __restrict__ G, size_t n2, int n_spin) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2;
+       i += (size_t)gridDim.x * blockDim.x) {
+    Dtot[i] = n_spin == 1 ? 2.0 * D[i] : D[i] + D[n2 + i];
+    G[i] = 0.0;
+    if (n_spin == 2) G[n2 + i] = 0.0;
+  }
+}
+
+// F[:,:,s] = G[:,:,s] + h_core   (compute_fock_matrix.jl:58)
+__global__ void fock_add_kernel(const double* __restrict__ G, const double* __restrict__ H,
+                                double* __restrict__ F, size_t n2, int n_spin) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2 * n_spin;
+       i += (size_t)gridDim.x * blockDim.x)
+    F[i] = G[i] + H[i % n2];
+}
+
+struct LinComb {
+  const double* m[kMaxPairs];
+  int count;
+};
+// out = sum_i c[i] * m_i   in index order (parts/diis.jl:52-54 starts from zeros)
+__global__ void lincomb_kernel(LinComb lc, const double* __restrict__ c, double* __restrict__ out,
+                               size_t n2) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n2;
+       e += (size_t)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    for (int i = 0; i < lc.count; ++i) v += c[i] * lc.m[i][e];
+    out[e] = v;
+  }
+}
+
+inline int blocks_for(size_t total) {
+  size_t b = (total + 255) / 256;
+  return (int)(b > 148 * 4 ? 148 * 4 : (b ? b : 1));
+}
+
+int gemm(scfb_handle_s* h, scfb_scf_state* st, cublasOperation_t ta, cublasOperation_t tb, int m,
+         int n, int k, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
+         double* Cm, int ldc) {
+  SCFB_BLAS(h, cublasDgemm(st->blas, ta, tb, m, n, k, &alpha, A, lda, B, ldb, &beta, Cm, ldc));
+  h->launches += 1;
+  return SCFB_OK;
+}
+
+// e = S D F - F D S   for one spin block (compute_pulay_error.jl:24)
+int pulay_block(scfb_handle_s* h, scfb_scf_state* st, const double* F, const double* D, double* E) {
+  const int n = st->n;
+  if (int rc = gemm(h, st, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, 1.0, D, n, F, n, 0.0, st->T1, n)) return rc;
+  if (int rc = gemm(h, st, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, 1.0, st->S, n, st->T1, n, 0.0, E, n)) return rc;
+  if (int rc = gemm(h, st, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, 1.0, D, n, st->S, n, 0.0, st->T2, n)) return rc;
+  return gemm(h, st, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, -1.0, F, n, st->T2, n, 1.0, E, n);
+}
+
+int require_state(scfb_handle_s* h) {
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  if (!h->scf) return scfb_fail(h, SCFB_ERR_STATE, "scfb_scf_setup has not been called");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cublasSetStream(h->scf->blas, h->stream);
+  cusolverDnSetStream(h->scf->solver, h->stream);
+  return SCFB_OK;
+}
+
+}  // namespace
+
+void scfb_scf_free(scfb_handle_s* h) {
+  scfb_scf_state* st = h->scf;
+  if (!st) return;
+  for (double* p : {st->S, st->H, st->F, st->Fnew, st->D, st->Dtot, st->G, st->E, st->C, st->eps,
+                    st->T1, st->T2, st->Bw, st->work, st->scal, st->coef, st->Fh, st->Eh, st->Dh})
+    cudaFree(p);
+  cudaFree(st->dev_info);
+  if (st->h_scal) cudaFreeHost(st->h_scal);
+  if (st->blas) cublasDestroy(st->blas);
+  if (st->solver) cusolverDnDestroy(st->solver);
+  delete st;
+  h->scf = nullptr;
+}
+
+extern "C" {
+
+int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core, double e_0e,
+                   int n_elec_a, int n_elec_b, int n_orb, int restricted, int n_diis_size) {
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  SCFB_REQUIRE(h, overlap && h_core, "null matrix pointer");
+  const int n = h->n;
+  SCFB_REQUIRE(h, n_orb >= 1 && n_orb <= n, "n_orb=%d outside [1, %d]", n_orb, n);
+  // compute_density.jl:8-10 asserts strictly fewer electrons than orbitals
+  SCFB_REQUIRE(h, n_elec_a >= 0 && n_elec_b >= 0 && n_elec_a < n_orb && n_elec_b < n_orb,
+               "n_elec of alpha and beta should be less than n_orb");
+  SCFB_REQUIRE(h, n_diis_size >= 1 && n_diis_size <= kMaxPairs, "n_diis_size must be in [1, %d]",
+               kMaxPairs);
+  SCFB_REQUIRE(h, !(restricted && n_elec_a != n_elec_b),
+               "restricted open-shell (ROHF effective Fock, compute_fock_matrix.jl:82-123) is not "
+               "on the device path; use restricted=false or the host path");
+  SCFB_CUDA(h, cudaSetDevice(h->device));
+  scfb_scf_free(h);
+  scfb_scf_state* st = new scfb_scf_state();
+  h->scf = st;
+  st->n = n;
+  st->n_orb = n_orb;
+  st->n_elec[0] = n_elec_a;
+  st->n_elec[1] = n_elec_b;
+  st->restricted = restricted != 0;
+  st->n_spin = st->restricted ? 1 : 2;  // compute_density.jl:24-27
+  st->e0 = e_0e;
+  st->cap = n_diis_size;
+  const size_t n2 = (size_t)n * n;
+  SCFB_BLAS(h, cublasCreate(&st->blas));
+  SCFB_SOLVER(h, cusolverDnCreate(&st->solver));
+  cublasSetStream(st->blas, h->stream);
+  cusolverDnSetStream(st->solver, h->stream);
+  auto alloc = [&](double** p, size_t count) { return cudaMalloc(p, count * sizeof(double)); };
+  SCFB_CUDA(h, alloc(&st->S, n2));
+  SCFB_CUDA(h, alloc(&st->H, n2));
+  SCFB_CUDA(h, alloc(&st->F, 2 * n2));
+  SCFB_CUDA(h, alloc(&st->Fnew, 2 * n2));
+  SCFB_CUDA(h, alloc(&st->D, 2 * n2));
+  SCFB_CUDA(h, alloc(&st->Dtot, n2));
+  SCFB_CUDA(h, alloc(&st->G, 2 * n2));
+  SCFB_CUDA(h, alloc(&st->E, 2 * n2));
+  SCFB_CUDA(h, alloc(&st->C, 2 * n2));
+  SCFB_CUDA(h, alloc(&st->eps, 2 * (size_t)n));
+  SCFB_CUDA(h, alloc(&st->T1, n2));
+  SCFB_CUDA(h, alloc(&st->T2, n2));
+  SCFB_CUDA(h, alloc(&st->Bw, n2));
+  SCFB_CUDA(h, alloc(&st->scal, kScal));
+  SCFB_CUDA(h, alloc(&st->coef, kMaxPairs));
+  SCFB_CUDA(h, alloc(&st->Fh, 2 * (size_t)st->cap * n2));
+  SCFB_CUDA(h, alloc(&st->Eh, 2 * (size_t)st->cap * n2));
+  SCFB_CUDA(h, alloc(&st->Dh, 2 * (size_t)st->cap * n2));
+  SCFB_CUDA(h, cudaMalloc(&st->dev_info, sizeof(int)));
+  SCFB_CUDA(h, cudaMallocHost(&st->h_scal, kScal * sizeof(double)));
+  SCFB_SOLVER(h, cusolverDnDsygvd_bufferSize(st->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
+                                             CUBLAS_FILL_MODE_LOWER, n, st->T1, n, st->Bw, n, st->eps,
+                                             &st->lwork));
+  SCFB_CUDA(h, alloc(&st->work, st->lwork > 0 ? st->lwork : 1));
+  SCFB_CUDA(h, cudaMemcpyAsync(st->S, overlap, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  SCFB_CUDA(h, cudaMemcpyAsync(st->H, h_core, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SCFB_OK;
+}
+
+int scfb_scf_n_spin(scfb_handle_t h, int* n_spin) {
+  if (int rc = require_state(h)) return rc;
+  if (n_spin) *n_spin = h->scf->n_spin;
+  return SCFB_OK;
+}
+
+int scfb_scf_set_density(scfb_handle_t h, int n_spin, const double* density) {
+  if (int rc = require_state(h)) return rc;
+  scfb_scf_state* st = h->scf;
+  SCFB_REQUIRE(h, density, "null density");
+  SCFB_REQUIRE(h, n_spin == st->n_spin, "density has %d spin blocks, problem needs %d", n_spin,
+               st->n_spin);
+  const size_t n2 = (size_t)st->n * st->n;
+  SCFB_CUDA(h, cudaMemcpyAsync(st->D, density, n2 * n_spin * sizeof(double), cudaMemcpyHostToDevice,
+                               h->stream));
+  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  st->have_density = true;
+  return SCFB_OK;
+}
+
+int scfb_scf_set_fock(scfb_handle_t h, int n_spin, const double* fock) {
+  if (int rc = require_state(h)) return rc;
+  scfb_scf_state* st = h->scf;
+  SCFB_REQUIRE(h, fock && n_spin == st->n_spin, "bad fock argument");
+  const size_t n2 = (size_t)st->n * st->n;
+  SCFB_CUDA(h, cudaMemcpyAsync(st->F, fock, n2 * n_spin * sizeof(double), cudaMemcpyHostToDevice,
+                               h->stream));
+  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  st->have_fock = true;
+  return SCFB_OK;
+}
+
+// compute_fock_matrix(problem, density) on the device-resident density:
+// Dtot, G = sum builders (here: this handle's J-K), energies, Fnew = G + h_core, E = SDF - FDS.
+int scfb_scf_fock(scfb_handle_t h, double* energies4, double* error_norm) {
+  if (int rc = require_state(h)) return rc;
+  scfb_scf_state* st = h->scf;
+  if (!st->have_density) return scfb_fail(h, SCFB_ERR_STATE, "no density: call scfb_scf_set_density");
+  const int n = st->n, ns = st->n_spin;
+  const size_t n2 = (size_t)n * n;
+  prepare_build_kernel<<<blocks_for(n2), 256, 0, h->stream>>>(st->D, st->Dtot, st->G, n2, ns);
+  h->launches += 1;
+  if (int rc = scfb_fock_jk_dev(h, ns, st->D, st->Dtot, st->G)) return rc;
+  fock_add_kernel<<<blocks_for(n2 * ns), 256, 0, h->stream>>>(st->G, st->H, st->Fnew, n2, ns);
+  h->launches += 1;
+  for (int s = 0; s < ns; ++s)
+    if (int rc = pulay_block(h, st, st->Fnew + s * n2, st->D + s * n2, st->E + s * n2)) return rc;
+  // scalars: [0] tr(h Dtot)  [1],[2] tr(G_s D_s)  [3],[4] <E_s, E_s>
+  TraceBatch tb{};
+  int k = 0;
+  tb.p[k++] = {st->H, st->Dtot, 1};
+  for (int s = 0; s < 2; ++s) {
+    const int ss = s < ns ? s : 0;
+    tb.p[k++] = {st->G + ss * n2, st->D + ss * n2, 1};
+  }
+  for (int s = 0; s < 2; ++s) {
+    const int ss = s < ns ? s : 0;
+    tb.p[k++] = {st->E + ss * n2, st->E + ss * n2, 0};
+  }
+  trace_kernel<<<k, 1024, 0, h->stream>>>(tb, n, st->scal);
+  h->launches += 1;
+  SCFB_CUDA(h, cudaGetLastError());
+  SCFB_CUDA(h, cudaMemcpyAsync(st->h_scal, st->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost,
+                               h->stream));
+  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  const double* v = st->h_scal;
+  const double e1 = v[0];
+  const double e2 = ns == 1 ? v[1] : 0.5 * (v[1] + v[2]);  // compute_fock_matrix.jl:44-53
+  if (energies4) {
+    energies4[0] = st->e0;
+    energies4[1] = e1;
+    energies4[2] = e2;
+    energies4[3] = st->e0 + e1 + e2;
+  }
+  if (error_norm) *error_norm = sqrt(ns == 1 ? v[3] : v[3] + v[4]);  // check_convergence.jl:18
+  return SCFB_OK;
+}
+
+// roothan_step's first two lines: orbitals from the iterate F, then the density.
+int scfb_scf_roothaan(scfb_handle_t h) {
+  if (int rc = require_state(h)) return rc;
+  scfb_scf_state* st = h->scf;
+  if (!st->have_fock) return scfb_fail(h, SCFB_ERR_STATE, "no Fock iterate on the device");
+  const int n = st->n, ns = st->n_spin;
+  const size_t n2 = (size_t)n * n;
+  for (int s = 0; s < ns; ++s) {
+    double* Cs = st->C + s * n2;
+    SCFB_CUDA(h, cudaMemcpyAsync(Cs, st->F + s * n2, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    SCFB_CUDA(h, cudaMemcpyAsync(st->Bw, st->S, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    SCFB_SOLVER(h, cusolverDnDsygvd(st->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
+                                    CUBLAS_FILL_MODE_LOWER, n, Cs, n, st->Bw, n, st->eps + s * n,
+                                    st->work, st->lwork, st->dev_info));
+    h->launches += 1;
+  }
+  int info = 0;
+  SCFB_CUDA(h, cudaMemcpyAsync(&info, st->dev_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (info != 0) return scfb_fail(h, SCFB_ERR_CUSOLVER, "Dsygvd failed: info=%d", info);
+  // D_s = C[:, 1:n_elec[s], s'] C[...]'   (compute_density.jl:16-32)
+  for (int s = 0; s < ns; ++s) {
+    const int nocc = st->n_elec[s];
+    double* Ds = st->D + s * n2;
+    if (nocc == 0) {
+      SCFB_CUDA(h, cudaMemsetAsync(Ds, 0, n2 * sizeof(double), h->stream));
+      continue;
+    }
+    const double* Cs = st->C + s * n2;
+    if (int rc = gemm(h, st, CUBLAS_OP_N, CUBLAS_OP_T, n, n, nocc, 1.0, Cs, n, Cs, n, 0.0, Ds, n)) return rc;
+  }
+  st->have_density = true;
+  return SCFB_OK;
+}
+
+// Push the newest (Fnew, E, D) of `spin` into the history (newest first, capacity n_diis_size:
+// DiisState.jl:26-34) and return the new first rows of both DIIS matrices:
+//   row_cdiis[j] = tr(e_1' e_j)                 (cDIIS.jl:126-127)
+//   row_ediis[j] = tr((F_1 - F_j)(D_1 - D_j))   (EDIIS.jl:87)
+int scfb_scf_diis_push(scfb_handle_t h, int spin, int* m_out, double* row_cdiis, double* row_ediis) {
+  if (int rc = require_state(h)) return rc;
+  scfb_scf_state* st = h->scf;
+  SCFB_REQUIRE(h, spin >= 0 && spin < st->n_spin, "spin %d out of range", spin);
+  const size_t n2 = (size_t)st->n * st->n;
+  std::vector<int>& ord = st->order[spin];
+  int slot;
+  if ((int)ord.size() == st->cap) {  // full: the oldest entry is dropped, its slot reused
+    slot = ord.back();
+    ord.pop_back();
+  } else {
+    std::vector<bool> used(st->cap, false);
+    for (int s : ord) used[s] = true;
+    slot = 0;
+    while (used[slot]) ++slot;
+  }
+  ord.insert(ord.begin(), slot);
+  const size_t off = ((size_t)spin * st->cap + slot) * n2;
+  SCFB_CUDA(h, cudaMemcpyAsync(st->Fh + off, st->Fnew + spin * n2, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  SCFB_CUDA(h, cudaMemcpyAsync(st->Eh + off, st->E + spin * n2, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  SCFB_CUDA(h, cudaMemcpyAsync(st->Dh + off, st->D + spin * n2, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  const int m = (int)ord.size();
+  TraceBatch tb{};
+  EdiisBatch eb{};
+  eb.f1 = st->Fh + off;
+  eb.d1 = st->Dh + off;
+  for (int j = 0; j < m; ++j) {
+    const size_t oj = ((size_t)spin * st->cap + ord[j]) * n2;
+    tb.p[j] = {st->Eh + off, st->Eh + oj, 0};  // tr(e1' ej) = <e1, ej>
+    eb.fj[j] = st->Fh + oj;
+    eb.dj[j] = st->Dh + oj;
+  }
+  trace_kernel<<<m, 1024, 0, h->stream>>>(tb, st->n, st->scal);
+  ediis_row_kernel<<<m, 1024, 0, h->stream>>>(eb, st->n, st->scal + kMaxPairs);
+  h->launches += 2;
+  SCFB_CUDA(h, cudaGetLastError());
+  SCFB_CUDA(h, cudaMemcpyAsync(st->h_scal, st->scal, 2 * kMaxPairs * sizeof(double),
+                               cudaMemcpyDeviceToHost, h->stream));
+  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (m_out) *m_out = m;
+  for (int j = 0; j < m; ++j) {
+    if (row_cdiis) row_cdiis[j] = st->h_scal[j];
+    if (row_ediis) row_ediis[j] = st->h_scal[kMaxPairs + j];
+  }
+  return SCFB_OK;
+}
+
+// F[:,:,spin] <- sum_{i<m} c[i] * Fhist_i  (newest first; zero coefficients are skipped, as the
+// masked entries are in parts/diis.jl:52-54)
+int scfb_scf_diis_extrapolate(scfb_handle_t h, int spin, int m, const double* c) {
+  if (int rc = require_state(h)) return rc;
+  scfb_scf_state* st = h->scf;
+  SCFB_REQUIRE(h, spin >= 0 && spin < st->n_spin, "spin %d out of range", spin);
+  SCFB_REQUIRE(h, c && m >= 1 && m <= (int)st->order[spin].size(), "m=%d outside the history (%d)", m,
+               (int)st->order[spin].size());
+  const size_t n2 = (size_t)st->n * st->n;
+  LinComb lc{};
+  double cc[kMaxPairs];
+  int k = 0;
+  for (int i = 0; i < m; ++i) {
+    if (c[i] == 0.0) continue;
+    lc.m[k] = st->Fh + ((size_t)spin * st->cap + st->order[spin][i]) * n2;
+    cc[k++] = c[i];
+  }
+  lc.count = k;
+  std::memcpy(st->h_scal + 2 * kMaxPairs, cc, k * sizeof(double));
+  SCFB_CUDA(h, cudaMemcpyAsync(st->coef, st->h_scal + 2 * kMaxPairs, kMaxPairs * sizeof(double),
+                               cudaMemcpyHostToDevice, h->stream));
+  lincomb_kernel<<<blocks_for(n2), 256, 0, h->stream>>>(lc, st->coef, st->F + spin * n2, n2);
+  h->launches += 1;
+  SCFB_CUDA(h, cudaGetLastError());
+  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));  // h_scal staging is reused by the next call
+  st->have_fock = true;
+  return SCFB_OK;
+}
+
+// DiisState.jl:40-50 — pops count+1 OLDEST entries when count > 0
+int scfb_scf_diis_purge(scfb_handle_t h, int spin, int count) {
+  if (int rc = require_state(h)) return rc;
+  scfb_scf_state* st = h->scf;
+  SCFB_REQUIRE(h, spin >= 0 && spin < st->n_spin && count >= 0, "bad purge arguments");
+  if (count == 0) return SCFB_OK;
+  std::vector<int>& ord = st->order[spin];
+  for (int i = 0; i < count + 1 && !ord.empty(); ++i) ord.pop_back();
+  return SCFB_OK;
+}
+
+int scfb_scf_diis_reset(scfb_handle_t h) {
+  if (int rc = require_state(h)) return rc;
+  h->scf->order[0].clear();
+  h->scf->order[1].clear();
+  return SCFB_OK;
+}
+
+// Use the newest Fock build as the iterate without extrapolation (accelerator == nothing).
+int scfb_scf_accept_fock(scfb_handle_t h) {
+  if (int rc = require_state(h)) return rc;
+  scfb_scf_state* st = h->scf;
+  const size_t n2 = (size_t)st->n * st->n;
+  SCFB_CUDA(h, cudaMemcpyAsync(st->F, st->Fnew, n2 * st->n_spin * sizeof(double),
+                               cudaMemcpyDeviceToDevice, h->stream));
+  st->have_fock = true;
+  return SCFB_OK;
+}
+
+int scfb_scf_get(scfb_handle_t h, int what, double* host_out) {
+  if (int rc = require_state(h)) return rc;
+  scfb_scf_state* st = h->scf;
+  SCFB_REQUIRE(h, host_out, "null output");
+  const size_t n = st->n, n2 = n * n, ns = st->n_spin;
+  const double* src = nullptr;
+  size_t count = 0;
+  switch (what) {
+    case SCFB_GET_FOCK: src = st->F; count = n2 * ns; break;
+    case SCFB_GET_FOCK_NEW: src = st->Fnew; count = n2 * ns; break;
+    case SCFB_GET_DENSITY: src = st->D; count = n2 * ns; break;
+    case SCFB_GET_ERROR: src = st->E; count = n2 * ns; break;
+    case SCFB_GET_ORBCOEFF: src = st->C; count = n2 * ns; break;  // all n columns per spin
+    case SCFB_GET_ORBEN: src = st->eps; count = n * ns; break;
+    default: return scfb_fail(h, SCFB_ERR_ARG, "unknown quantity %d", what);
+  }
+  SCFB_CUDA(h, cudaMemcpyAsync(host_out, src, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SCFB_OK;
+}
+
+// ---- stateless host-pointer twins of the reference's plain functions ---------------------
+// compute_pulay_error(fock, density, overlap) -> error   (compute_pulay_error.jl:1-25)
+int scfb_pulay_error(scfb_handle_t h, int n_spin, const double* fock, const double* density,
+                     const double* overlap, double* error_out) {
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  SCFB_REQUIRE(h, (n_spin == 1 || n_spin == 2) && fock && density && overlap && error_out,
+               "bad arguments");
+  SCFB_CUDA(h, cudaSetDevice(h->device));
+  const int n = h->n;
+  const size_t n2 = (size_t)n * n;
+  scfb_scf_state tmp;  // borrows a cuBLAS handle + scratch just for this call
+  double* buf = nullptr;
+  SCFB_CUDA(h, cudaMalloc(&buf, (3 + 3 * (size_t)n_spin) * n2 * sizeof(double)));
+  tmp.n = n;
+  tmp.S = buf;
+  tmp.T1 = buf + n2;
+  tmp.T2 = buf + 2 * n2;
+  double* F = buf + 3 * n2;
+  double* D = F + n_spin * n2;
+  double* E = D + n_spin * n2;
+  int rc = SCFB_OK;
+  if (cublasCreate(&tmp.blas) != CUBLAS_STATUS_SUCCESS) {
+    cudaFree(buf);
+    return scfb_fail(h, SCFB_ERR_CUSOLVER, "cublasCreate failed");
+  }
+  cublasSetStream(tmp.blas, h->stream);
+  cudaMemcpyAsync(tmp.S, overlap, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(F, fock, n_spin * n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(D, density, n_spin * n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  for (int s = 0; s < n_spin && rc == SCFB_OK; ++s)
+    rc = pulay_block(h, &tmp, F + s * n2, D + s * n2, E + s * n2);
+  cudaMemcpyAsync(error_out, E, n_spin * n2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cublasDestroy(tmp.blas);
+  cudaFree(buf);
+  if (rc) return rc;
+  if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "pulay_error: %s", cudaGetErrorString(e));
+  return SCFB_OK;
+}
+
+// compute_orbitals(problem, fock) (compute_orbitals.jl:4-19): per spin F C = S C eps with
+// LAPACK sygvd semantics (C' S C = I, ascending eps); first n_orb columns are returned.
+int scfb_sygvd(scfb_handle_t h, int n_spin, int n_orb, const double* fock, const double* overlap,
+               double* orben_out, double* orbcoeff_out) {
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  const int n = h->n;
+  SCFB_REQUIRE(h, (n_spin == 1 || n_spin == 2) && fock && overlap && orben_out && orbcoeff_out &&
+                      n_orb >= 1 && n_orb <= n, "bad arguments");
+  SCFB_CUDA(h, cudaSetDevice(h->device));
+  const size_t n2 = (size_t)n * n;
+  cusolverDnHandle_t solver = nullptr;
+  if (cusolverDnCreate(&solver) != CUSOLVER_STATUS_SUCCESS)
+    return scfb_fail(h, SCFB_ERR_CUSOLVER, "cusolverDnCreate failed");
+  cusolverDnSetStream(solver, h->stream);
+  double* buf = nullptr;
+  int* info_d = nullptr;
+  int lwork = 0, rc = SCFB_OK, info = 0;
+  cudaError_t e = cudaMalloc(&buf, (2 * n2 + n) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&info_d, sizeof(int));
+  double *A = buf, *B = buf + n2, *W = buf + 2 * n2, *work = nullptr;
+  if (e == cudaSuccess &&
+      cusolverDnDsygvd_bufferSize(solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
+                                  CUBLAS_FILL_MODE_LOWER, n, A, n, B, n, W, &lwork) != CUSOLVER_STATUS_SUCCESS)
+    rc = scfb_fail(h, SCFB_ERR_CUSOLVER, "Dsygvd_bufferSize failed");
+  if (e == cudaSuccess && rc == SCFB_OK) e = cudaMalloc(&work, (lwork > 0 ? lwork : 1) * sizeof(double));
+  for (int s = 0; s < n_spin && rc == SCFB_OK && e == cudaSuccess; ++s) {
+    cudaMemcpyAsync(A, fock + s * n2, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(B, overlap, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (cusolverDnDsygvd(solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER,
+                         n, A, n, B, n, W, work, lwork, info_d) != CUSOLVER_STATUS_SUCCESS)
+      rc = scfb_fail(h, SCFB_ERR_CUSOLVER, "Dsygvd failed to launch");
+    h->launches += 1;
+    cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(orben_out + (size_t)s * n_orb, W, n_orb * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(orbcoeff_out + (size_t)s * n * n_orb, A, (size_t)n * n_orb * sizeof(double),
+                    cudaMemcpyDeviceToHost, h->stream);
+    e = cudaStreamSynchronize(h->stream);
+    if (rc == SCFB_OK && info != 0) rc = scfb_fail(h, SCFB_ERR_CUSOLVER, "Dsygvd: info=%d", info);
+  }
+  cudaFree(work);
+  cudaFree(info_d);
+  cudaFree(buf);
+  cusolverDnDestroy(solver);
+  if (rc) return rc;
+  if (e != cudaSuccess) return scfb_fail(h, e == cudaErrorMemoryAllocation ? SCFB_ERR_OOM : SCFB_ERR_CUDA,
+                                         "sygvd: %s", cudaGetErrorString(e));
+  return SCFB_OK;
+}
+
+}  // extern "C"

@@ -294,11 +294,11 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
   return SCFB_OK;
 }
 
-int scfb_launch_accumulate(scfb_handle_s* h, int n_spin, double* d_out) {
+int scfb_launch_accumulate(scfb_handle_s* h, int n_spin, const double* d_jk, double* d_out) {
   const size_t total = (size_t)h->n * h->n * n_spin;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  accumulate_kernel<<<blocks, 256, 0, h->stream>>>(h->jk, d_out, h->n, n_spin);
+  accumulate_kernel<<<blocks, 256, 0, h->stream>>>(d_jk, d_out, h->n, n_spin);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return scfb_fail(h, SCFB_ERR_CUDA, "accumulate_kernel launch: %s", cudaGetErrorString(e));

@@ -103,6 +103,8 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
   h->d_out = h->d_density + 3 * n2;
   CREATE_CUDA(cudaMalloc(&h->jk, 3 * n2 * sizeof(double)));
   CREATE_CUDA(cudaMemsetAsync(h->jk, 0, 3 * n2 * sizeof(double), h->stream));
+  h->jk_sum = h->jk;
+  if (n_ranks > 1) CREATE_CUDA(cudaMalloc(&h->jk_sum, 3 * n2 * sizeof(double)));
   if (h->kpart_elems) CREATE_CUDA(cudaMalloc(&h->kpart, h->kpart_elems * sizeof(double)));
   CREATE_CUDA(cudaMallocHost(&h->h_stage, 5 * n2 * sizeof(double)));
   CREATE_CUDA(cudaStreamSynchronize(h->stream));
@@ -118,6 +120,7 @@ int scfb_destroy(scfb_handle_t h) {
   scfb_comm_destroy(h);
   cudaFree(h->eri);
   cudaFree(h->d_density);
+  if (h->jk_sum != h->jk) cudaFree(h->jk_sum);
   cudaFree(h->jk);
   cudaFree(h->kpart);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -225,9 +228,12 @@ int scfb_fock_jk_dev(scfb_handle_t h, int n_spin, const double* d_density,
   if (int rc = check_build_args(h, n_spin, d_density, d_total_density, d_out)) return rc;
   if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
   if (int rc = scfb_launch_jk_full(h, n_spin, d_density, d_total_density)) return rc;
-  if (h->n_ranks > 1 && h->nccl_comm)
+  const double* jk_final = h->jk;
+  if (h->n_ranks > 1 && h->nccl_comm) {
     if (int rc = scfb_comm_allreduce_jk(h, n_spin)) return rc;
-  if (int rc = scfb_launch_accumulate(h, n_spin, d_out)) return rc;
+    jk_final = h->jk_sum;
+  }
+  if (int rc = scfb_launch_accumulate(h, n_spin, jk_final, d_out)) return rc;
   if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
   return SCFB_OK;
 }
@@ -254,11 +260,14 @@ int scfb_jk_split(scfb_handle_t h, int n_spin, const double* density, const doub
   if (int rc = stage_inputs(h, n_spin, density, total_density, nullptr)) return rc;
   if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
   if (int rc = scfb_launch_jk_full(h, n_spin, h->d_density, h->d_total)) return rc;
-  if (h->n_ranks > 1 && h->nccl_comm)
+  const double* jk_final = h->jk;
+  if (h->n_ranks > 1 && h->nccl_comm) {
     if (int rc = scfb_comm_allreduce_jk(h, n_spin)) return rc;
+    jk_final = h->jk_sum;
+  }
   if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
   const size_t n2 = (size_t)h->n * h->n;
-  SCFB_CUDA(h, cudaMemcpyAsync(h->h_stage, h->jk, (1 + n_spin) * n2 * sizeof(double),
+  SCFB_CUDA(h, cudaMemcpyAsync(h->h_stage, jk_final, (1 + n_spin) * n2 * sizeof(double),
                                cudaMemcpyDeviceToHost, h->stream));
   SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
   std::memcpy(J, h->h_stage, n2 * sizeof(double));

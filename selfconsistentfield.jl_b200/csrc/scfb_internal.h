@@ -27,7 +27,8 @@ struct scfb_handle_s {
   double* d_density = nullptr;  // n*n*2   (host-pointer API staging)
   double* d_total = nullptr;    // n*n
   double* d_out = nullptr;      // n*n*2
-  double* jk = nullptr;         // [J | K_0 | K_1], 3*n*n, zero outside owned columns
+  double* jk = nullptr;         // [J | K_0 | K_1], 3*n*n, this rank's partial: zero outside owned columns
+  double* jk_sum = nullptr;     // allreduce result (n_ranks > 1); == jk when single rank
   double* kpart = nullptr;      // per-(nu, c-chunk) partial K rows
   uint64_t kpart_elems = 0;
   double* h_stage = nullptr;    // pinned host staging, 5*n*n
@@ -81,7 +82,7 @@ inline void scfb_split_range(int n, int rank, int n_ranks, int* lo, int* hi) {
 // jk_full.cu
 int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
                         const double* d_total);            // fills h->jk for owned columns
-int scfb_launch_accumulate(scfb_handle_s* h, int n_spin, double* d_out);  // out += J - K_s
+int scfb_launch_accumulate(scfb_handle_s* h, int n_spin, const double* d_jk, double* d_out);  // out += J - K_s
 uint64_t scfb_kpart_elems_full(int n, int n_slabs);
 // eri_gen.cu
 int scfb_launch_generate_full(scfb_handle_s* h, int family, uint64_t seed, const double* d_aux);
