@@ -17,13 +17,15 @@
  *   src/types/ScfProblem.jl:2-9                 abstract TwoElectronBuilder + add_2e_term!
  *   src/algorithms/JKBuilderFromTensor.jl:7-9   ERI storage           -> scfb_create / scfb_eri_*
  *   src/algorithms/JKBuilderFromTensor.jl:22-51 add_2e_term!          -> scfb_fock_jk
- *   src/parts/compute_fock_matrix.jl:8-71       Fock assembly/energies-> scfb_fock_assemble
- *   src/parts/compute_pulay_error.jl:1-25       S D F - F D S         -> scfb_pulay_error
- *   src/parts/compute_orbitals.jl:4-19          eigen(F, S)           -> scfb_sygvd
- *   src/parts/compute_density.jl:4-35           C_occ C_occ'          -> scfb_density
- *   src/algorithms/cDIIS.jl:123-127             B row tr(e1' ej)      -> scfb_diis_push / _row
- *   src/parts/diis.jl:42-55                     F <- sum c_i F_i      -> scfb_diis_extrapolate
- *   examples/HartreeFock.jl:88-95               J/K energy split      -> scfb_jk_energies
+ *   src/parts/compute_fock_matrix.jl:8-71       Fock assembly/energies-> scfb_scf_fock
+ *   src/parts/compute_pulay_error.jl:1-25       S D F - F D S         -> scfb_pulay_error, scfb_scf_fock
+ *   src/parts/compute_orbitals.jl:4-19          eigen(F, S)           -> scfb_sygvd, scfb_scf_roothaan
+ *   src/parts/compute_density.jl:4-35           C_occ C_occ'          -> scfb_scf_roothaan
+ *   src/parts/check_convergence.jl:18           ||e||_F               -> scfb_scf_fock
+ *   src/algorithms/cDIIS.jl:123-127             B row tr(e1' ej)      -> scfb_scf_diis_push
+ *   src/algorithms/EDIIS.jl:87                  tr((Fi-Fj)(Di-Dj))    -> scfb_scf_diis_push
+ *   src/parts/diis.jl:42-55                     F <- sum c_i F_i      -> scfb_scf_diis_extrapolate
+ *   src/types/DiisState.jl:40-50                purge                 -> scfb_scf_diis_purge
  */
 #ifndef SCF_B200_H
 #define SCF_B200_H
@@ -100,6 +102,47 @@ int scfb_jk_split(scfb_handle_t h, int n_spin, const double* density,
 int scfb_last_build_ms(scfb_handle_t h, double* stream_ms, double* total_ms);
 /* Number of kernels this library launched on this handle since creation. */
 int scfb_launch_count(scfb_handle_t h, uint64_t* launches);
+
+/* ---- device-resident SCF step (rows a4-a9 of SURVEY.md 8) ---------------------------
+ * The handle keeps S, h_core, the density, the Fock iterate, the Pulay error, the orbitals
+ * and the DIIS history in HBM; per iteration only scalars and DIIS rows cross PCIe.  The
+ * caller keeps the control flow of run_scf.jl:21-49 and the <= 6x6 coefficient solves
+ * (cDIIS.jl:33-63, EDIIS.jl:20-44).  RHF (restricted, closed shell: 1 spin block) and UHF
+ * (2 spin blocks); ROHF is not on the device path. */
+#define SCFB_GET_FOCK 0      /* the iterate F (after extrapolation)   (n,n,n_spin) */
+#define SCFB_GET_FOCK_NEW 1  /* Fock matrix of the newest build       (n,n,n_spin) */
+#define SCFB_GET_DENSITY 2   /*                                       (n,n,n_spin) */
+#define SCFB_GET_ERROR 3     /* S D F - F D S of the newest build     (n,n,n_spin) */
+#define SCFB_GET_ORBCOEFF 4  /* all n eigenvectors per spin           (n,n,n_spin) */
+#define SCFB_GET_ORBEN 5     /* all n eigenvalues per spin            (n,n_spin)   */
+#define SCFB_GET_ORBCOEFF_PREV 6 /* same three of the previous Roothaan step: what     */
+#define SCFB_GET_ORBEN_PREV 7    /* run_scf.jl:52-58 returns when the loop breaks on   */
+#define SCFB_GET_DENSITY_PREV 8  /* convergence (:40 precedes :48)                     */
+int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core, double e_0e,
+                   int n_elec_a, int n_elec_b, int n_orb, int restricted, int n_diis_size);
+int scfb_scf_n_spin(scfb_handle_t h, int* n_spin);
+int scfb_scf_set_density(scfb_handle_t h, int n_spin, const double* density);
+int scfb_scf_set_fock(scfb_handle_t h, int n_spin, const double* fock);
+/* compute_fock_matrix.jl:8-71 on the resident density: energies4 = {0e, 1e, 2e, total},
+ * error_norm = Frobenius norm of the Pulay error over all spins (check_convergence.jl:18). */
+int scfb_scf_fock(scfb_handle_t h, double* energies4, double* error_norm);
+/* Roothaan.jl:5-6: orbitals of the iterate F (cuSOLVER Dsygvd), then the density. */
+int scfb_scf_roothaan(scfb_handle_t h);
+/* Push the newest (F, e, D) of `spin` into the history (newest first, capacity
+ * n_diis_size) and return the new first rows, length *m: tr(e1' ej) and
+ * tr((F1-Fj)(D1-Dj)).  Either row pointer may be NULL. */
+int scfb_scf_diis_push(scfb_handle_t h, int spin, int* m, double* row_cdiis, double* row_ediis);
+/* F[:,:,spin] <- sum_{i<m} c[i] * F_i over the history, newest first (diis.jl:52-54). */
+int scfb_scf_diis_extrapolate(scfb_handle_t h, int spin, int m, const double* c);
+int scfb_scf_diis_purge(scfb_handle_t h, int spin, int count); /* DiisState.jl:40-50 */
+int scfb_scf_diis_reset(scfb_handle_t h);
+int scfb_scf_accept_fock(scfb_handle_t h); /* iterate <- newest Fock (no accelerator) */
+int scfb_scf_get(scfb_handle_t h, int what, double* host_out);
+/* Stateless host-pointer twins of the reference's plain functions. */
+int scfb_pulay_error(scfb_handle_t h, int n_spin, const double* fock, const double* density,
+                     const double* overlap, double* error_out);
+int scfb_sygvd(scfb_handle_t h, int n_spin, int n_orb, const double* fock, const double* overlap,
+               double* orben_out, double* orbcoeff_out);
 
 /* ---- multi-GPU exchange (one process per GPU) ------------------------- */
 /* Rank 0 calls scfb_comm_unique_id and ships the 128 bytes to the other ranks by any

@@ -50,6 +50,20 @@ _SIGNATURES = {
     "scfb_jk_split": [_h, C.c_int, _dp, _dp, _dp, _dp],
     "scfb_last_build_ms": [_h, _dp, _dp],
     "scfb_launch_count": [_h, C.POINTER(C.c_uint64)],
+    "scfb_scf_setup": [_h, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
+    "scfb_scf_n_spin": [_h, C.POINTER(C.c_int)],
+    "scfb_scf_set_density": [_h, C.c_int, _dp],
+    "scfb_scf_set_fock": [_h, C.c_int, _dp],
+    "scfb_scf_fock": [_h, _dp, _dp],
+    "scfb_scf_roothaan": [_h],
+    "scfb_scf_diis_push": [_h, C.c_int, C.POINTER(C.c_int), _dp, _dp],
+    "scfb_scf_diis_extrapolate": [_h, C.c_int, C.c_int, _dp],
+    "scfb_scf_diis_purge": [_h, C.c_int, C.c_int],
+    "scfb_scf_diis_reset": [_h],
+    "scfb_scf_accept_fock": [_h],
+    "scfb_scf_get": [_h, C.c_int, _dp],
+    "scfb_pulay_error": [_h, C.c_int, _dp, _dp, _dp, _dp],
+    "scfb_sygvd": [_h, C.c_int, C.c_int, _dp, _dp, _dp, _dp],
     "scfb_comm_unique_id": [C.c_char_p],
     "scfb_comm_init": [_h, C.c_char_p],
 }

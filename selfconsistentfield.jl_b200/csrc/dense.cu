@@ -30,6 +30,7 @@ struct scfb_scf_state {
   double *F = nullptr, *Fnew = nullptr, *D = nullptr;      // 2 n^2 each
   double *Dtot = nullptr, *G = nullptr, *E = nullptr;      // n^2, 2 n^2, 2 n^2
   double *C = nullptr, *eps = nullptr;                     // 2 n^2, 2 n
+  double *Cprev = nullptr, *epsprev = nullptr, *Dprev = nullptr;  // previous Roothaan step
   double *T1 = nullptr, *T2 = nullptr, *Bw = nullptr;      // n^2 scratch
   double *work = nullptr;
   int lwork = 0;
@@ -198,7 +199,8 @@ void scfb_scf_free(scfb_handle_s* h) {
   scfb_scf_state* st = h->scf;
   if (!st) return;
   for (double* p : {st->S, st->H, st->F, st->Fnew, st->D, st->Dtot, st->G, st->E, st->C, st->eps,
-                    st->T1, st->T2, st->Bw, st->work, st->scal, st->coef, st->Fh, st->Eh, st->Dh})
+                    st->T1, st->T2, st->Bw, st->work, st->scal, st->coef, st->Fh, st->Eh, st->Dh,
+                    st->Cprev, st->epsprev, st->Dprev})
     cudaFree(p);
   cudaFree(st->dev_info);
   if (st->h_scal) cudaFreeHost(st->h_scal);
@@ -252,6 +254,9 @@ int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core,
   SCFB_CUDA(h, alloc(&st->E, 2 * n2));
   SCFB_CUDA(h, alloc(&st->C, 2 * n2));
   SCFB_CUDA(h, alloc(&st->eps, 2 * (size_t)n));
+  SCFB_CUDA(h, alloc(&st->Cprev, 2 * n2));
+  SCFB_CUDA(h, alloc(&st->epsprev, 2 * (size_t)n));
+  SCFB_CUDA(h, alloc(&st->Dprev, 2 * n2));
   SCFB_CUDA(h, alloc(&st->T1, n2));
   SCFB_CUDA(h, alloc(&st->T2, n2));
   SCFB_CUDA(h, alloc(&st->Bw, n2));
@@ -357,6 +362,10 @@ int scfb_scf_roothaan(scfb_handle_t h) {
   if (!st->have_fock) return scfb_fail(h, SCFB_ERR_STATE, "no Fock iterate on the device");
   const int n = st->n, ns = st->n_spin;
   const size_t n2 = (size_t)n * n;
+  // keep the previous step's orbitals/density: run_scf.jl:52-58 returns those on convergence
+  SCFB_CUDA(h, cudaMemcpyAsync(st->Cprev, st->C, 2 * n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  SCFB_CUDA(h, cudaMemcpyAsync(st->epsprev, st->eps, 2 * (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  SCFB_CUDA(h, cudaMemcpyAsync(st->Dprev, st->D, 2 * n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   for (int s = 0; s < ns; ++s) {
     double* Cs = st->C + s * n2;
     SCFB_CUDA(h, cudaMemcpyAsync(Cs, st->F + s * n2, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -508,6 +517,9 @@ int scfb_scf_get(scfb_handle_t h, int what, double* host_out) {
     case SCFB_GET_ERROR: src = st->E; count = n2 * ns; break;
     case SCFB_GET_ORBCOEFF: src = st->C; count = n2 * ns; break;  // all n columns per spin
     case SCFB_GET_ORBEN: src = st->eps; count = n * ns; break;
+    case SCFB_GET_ORBCOEFF_PREV: src = st->Cprev; count = n2 * ns; break;
+    case SCFB_GET_ORBEN_PREV: src = st->epsprev; count = n * ns; break;
+    case SCFB_GET_DENSITY_PREV: src = st->Dprev; count = n2 * ns; break;
     default: return scfb_fail(h, SCFB_ERR_ARG, "unknown quantity %d", what);
   }
   SCFB_CUDA(h, cudaMemcpyAsync(host_out, src, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -118,6 +118,7 @@ int scfb_destroy(scfb_handle_t h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   scfb_comm_destroy(h);
+  scfb_scf_free(h);
   cudaFree(h->eri);
   cudaFree(h->d_density);
   if (h->jk_sum != h->jk) cudaFree(h->jk_sum);

@@ -10,6 +10,8 @@
 
 #include "../../include/scf_b200.h"
 
+struct scfb_scf_state;  // dense.cu
+
 struct scfb_handle_s {
   int n = 0;             // n_bas
   int layout = SCFB_LAYOUT_FULL;
@@ -38,6 +40,8 @@ struct scfb_handle_s {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // build start, stream end, build end
   bool timed = false;
   uint64_t launches = 0;
+
+  scfb_scf_state* scf = nullptr;  // device-resident SCF step (scfb_scf_setup)
 
   void* nccl_comm = nullptr;  // ncclComm_t when n_ranks > 1 and initialised
 
@@ -89,3 +93,5 @@ int scfb_launch_generate_full(scfb_handle_s* h, int family, uint64_t seed, const
 // comm.cu
 int scfb_comm_allreduce_jk(scfb_handle_s* h, int n_spin);
 int scfb_comm_destroy(scfb_handle_s* h);
+// dense.cu
+void scfb_scf_free(scfb_handle_s* h);

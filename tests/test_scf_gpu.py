@@ -1,0 +1,214 @@
+"""GPU parity of the dense steps around the Fock build and of the
+full SCF loop driven through the product's host mirror of the reference API, against the
+CPU oracle and the reference's golden energies.  Energies: 1e-10 Eh (north star)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+import scf_b200
+from oracle import scf_oracle as o
+from oracle import synth
+from scf_b200 import scf as S
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(x, ref):
+    return np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+def oracle_problem(golden_dir, stem, restricted):
+    system, integrals = o.load_integral_npz(os.path.join(golden_dir, stem + ".npz"))
+    return o.assemble_hf_problem(system, integrals, restricted=restricted), integrals
+
+
+def cuda_problem(golden_dir, stem, restricted):
+    system, integrals = scf_b200.load_integral_npz(os.path.join(golden_dir, stem + ".npz"))
+    return scf_b200.assemble_hf_problem(system, integrals, restricted=restricted), system
+
+
+# ---- stateless twins ---------------------------------------------------------------------
+@pytest.mark.parametrize("n,n_spin", [(9, 1), (16, 2), (65, 2)])
+def test_pulay_error_matches_oracle(n, n_spin):
+    rng = np.random.default_rng(n)
+    f = rng.standard_normal((n, n, n_spin))
+    d = rng.standard_normal((n, n, n_spin))      # literal S D F - F D S, no symmetry assumed
+    s = rng.standard_normal((n, n))
+    b = scf_b200.JKBuilderCUDA(n)
+    e = S.compute_pulay_error(f, d, s, builder=b)
+    assert rel_err(e, o.compute_pulay_error(f, d, s)) < 1e-12
+    e2 = S.compute_pulay_error(f[:, :, 0], d[:, :, 0], s, builder=b)     # 2-D method
+    assert e2.shape == (n, n) and rel_err(e2, o.compute_pulay_error(f[:, :, 0], d[:, :, 0], s)) < 1e-12
+    b.close()
+
+
+@pytest.mark.parametrize("n,n_orb", [(9, 9), (32, 20), (128, 128)])
+def test_sygvd_has_lapack_semantics(n, n_orb):
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n))
+    s = a @ a.T / n + np.eye(n)
+    f = rng.standard_normal((n, n, 2))
+    f = f + f.transpose(1, 0, 2)
+    b = scf_b200.JKBuilderCUDA(n)
+    problem = S.ScfProblem(s, (1, 1), n_orb, False, {}, {}, {"jk": b})
+    orben, c = S.compute_orbitals(problem, f)
+    assert orben.shape == (n_orb, 2) and c.shape == (n, n_orb, 2)
+    for sp in range(2):
+        w = scipy.linalg.eigh(f[:, :, sp], s, eigvals_only=True)
+        assert np.abs(orben[:, sp] - w[:n_orb]).max() < 1e-11 * np.abs(w).max()
+        cs = c[:, :, sp]
+        assert np.abs(cs.T @ s @ cs - np.eye(n_orb)).max() < 1e-11          # C' S C = I
+        resid = f[:, :, sp] @ cs - s @ cs * orben[:, sp]
+        assert np.abs(resid).max() < 1e-10 * np.abs(f).max()
+    b.close()
+
+
+# ---- one device-resident SCF step against the oracle --------------------------------------
+@pytest.mark.parametrize("stem,restricted", [("integrals_be_3-21g", True), ("integrals_be_3-21g", False),
+                                             ("integrals_c_3-21g", False)])
+def test_device_fock_step_matches_oracle(golden_dir, stem, restricted):
+    op, _ = oracle_problem(golden_dir, stem, restricted)
+    cp, _ = cuda_problem(golden_dir, stem, restricted)
+    density = o.compute_guess_hcore(op)
+    if not restricted:
+        o.break_spin_symmetry(density)
+    f_ref, e_ref, en_ref = o.compute_fock_matrix(op, density)
+    dev = S.DeviceScf(cp, cp.terms_2e["coulomb+exchange"])
+    dev.set_density(density)
+    energies, norm = dev.fock()
+    for k in ("0e", "1e", "2e", "total"):
+        assert abs(energies[k] - en_ref[k]) < 1e-11
+    assert abs(norm - np.linalg.norm(e_ref.reshape(-1))) < 1e-12
+    assert rel_err(dev.get(dev.FOCK_NEW), f_ref) < 1e-12
+    assert np.abs(dev.get(dev.ERROR) - e_ref).max() < 1e-12 * np.abs(f_ref).max()
+    # Roothaan step from that Fock matrix: same density as the oracle's LAPACK path
+    # (Be: occupied levels are non-degenerate at this point)
+    if "be" in stem:
+        dev.accept_fock()
+        dev.roothaan()
+        _, c_ref = o.compute_orbitals(op, f_ref)
+        d_ref = o.compute_density(op, c_ref)
+        assert np.abs(dev.get(dev.DENSITY) - d_ref).max() < 1e-10
+        eps = dev.get(dev.ORBEN)
+        w = scipy.linalg.eigh(f_ref[:, :, 0], op.overlap, eigvals_only=True)
+        assert np.abs(eps[:, 0] - w).max() < 1e-11
+
+
+def test_device_diis_rows_extrapolation_and_purge(golden_dir):
+    cp, _ = cuda_problem(golden_dir, "integrals_c_3-21g", False)
+    op, _ = oracle_problem(golden_dir, "integrals_c_3-21g", False)
+    dev = S.DeviceScf(cp, cp.terms_2e["coulomb+exchange"], n_diis_size=3)
+    dev.set_density(o.compute_guess_hcore(op))
+    hist = []
+    for it in range(5):
+        dev.fock()
+        f, e, d = dev.get(dev.FOCK_NEW), dev.get(dev.ERROR), dev.get(dev.DENSITY)
+        hist.insert(0, (f, e, d))
+        del hist[3:]
+        for sp in range(2):
+            rc, re = dev.diis_push(sp)
+            assert len(rc) == len(hist)
+            for j, (fj, ej, dj) in enumerate(hist):
+                assert abs(rc[j] - np.sum(hist[0][1][:, :, sp] * ej[:, :, sp])) < 1e-12 * max(1, abs(rc[0]))
+                ref = np.trace((hist[0][0][:, :, sp] - fj[:, :, sp]) @ (hist[0][2][:, :, sp] - dj[:, :, sp]))
+                assert abs(re[j] - ref) < 1e-12 * max(1.0, abs(ref))
+        c = np.array([0.7, 0.5, -0.2][:len(hist)])
+        c[0] += 1 - c.sum()
+        for sp in range(2):
+            dev.diis_extrapolate(sp, c)
+        f_it = dev.get(dev.FOCK)
+        ref = sum(ci * h[0] for ci, h in zip(c, hist))
+        assert rel_err(f_it, ref) < 1e-13
+        dev.roothaan()
+    # purge pops count+1 oldest (DiisState.jl:44-49)
+    dev.diis_purge(0, 1)
+    rc, _ = dev.diis_push(0)
+    assert len(rc) == 2
+    dev.diis_reset()
+    rc, _ = dev.diis_push(1)
+    assert len(rc) == 1
+
+
+# ---- the reference's golden energies through the product's run_scf ------------------------
+@pytest.mark.parametrize("name", ["rhf_be_321g", "uhf_be_321g", "rohf_c_321g", "uhf_c_321g"])
+def test_run_scf_reproduces_reference_goldens(golden_dir, name, capsys):
+    case = json.load(open(os.path.join(golden_dir, "golden_energies.json")))[name]
+    problem, system = cuda_problem(golden_dir, case["file"], case["restricted"])
+    guess = scf_b200.compute_guess(problem, system["coords"], system["atom_numbers"], method="hcore")
+    if (not problem.restricted) and S.is_closed_shell(problem):
+        scf_b200.break_spin_symmetry(guess)
+    res = scf_b200.run_scf(problem, guess)
+    assert res["converged"]
+    assert res["mode"] == ("generic" if name == "rohf_c_321g" else "device")
+    # the reference's assertion (test/functionality_hartee_fock.jl:18,24,30,36)
+    assert res["energies"]["total"] == pytest.approx(case["e_total"], rel=1e-9, abs=0)
+    out = capsys.readouterr().out
+    assert "iter" in out and "scf_error" in out          # run_scf.jl:19-20 table
+
+
+@pytest.mark.parametrize("name", ["rhf_be_321g", "uhf_be_321g", "uhf_c_321g"])
+def test_tight_convergence_energy_within_1e10(golden_dir, name):
+    """North star: converged energies match to 1e-10 Eh (same-iterate comparison with the
+    thresholds tightened)."""
+    case = json.load(open(os.path.join(golden_dir, "golden_energies.json")))[name]
+    kw = dict(max_error_norm=1e-10, max_energy_total_change=1e-12, max_iter=200, verbose=False)
+    problem, system = cuda_problem(golden_dir, case["file"], case["restricted"])
+    guess = scf_b200.compute_guess(problem)
+    op, _ = oracle_problem(golden_dir, case["file"], case["restricted"])
+    og = o.compute_guess_hcore(op)
+    if not problem.restricted:
+        scf_b200.break_spin_symmetry(guess)
+        o.break_spin_symmetry(og)
+    res = scf_b200.run_scf(problem, guess, **kw)
+    ref = o.run_scf(op, og, **{k: v for k, v in kw.items() if k != "verbose"})
+    assert res["converged"] and ref["converged"]
+    assert abs(res["energies_newest"]["total"] - ref["energies_newest"]["total"]) < 1e-10
+    assert abs(res["energies_newest"]["total"] - case["e_total"]) < 1e-9 * abs(case["e_total"])
+
+
+def test_generic_and_device_modes_agree(golden_dir):
+    kw = dict(max_error_norm=1e-10, max_energy_total_change=1e-12, max_iter=200, verbose=False)
+    problem, _ = cuda_problem(golden_dir, "integrals_be_3-21g", True)
+    guess = scf_b200.compute_guess(problem)
+    a = scf_b200.run_scf(problem, guess, mode="device", **kw)
+    b = scf_b200.run_scf(problem, guess, mode="generic", **kw)
+    assert a["converged"] and b["converged"] and a["mode"] == "device" and b["mode"] == "generic"
+    assert abs(a["energies_newest"]["total"] - b["energies_newest"]["total"]) < 1e-10
+    assert a["fock"].shape == b["fock"].shape == (9, 9, 1)
+    assert a["orbcoeff"].shape == b["orbcoeff"].shape
+    assert np.abs(a["density"] - b["density"]).max() < 1e-8
+
+
+@pytest.mark.parametrize("n", [16, 64])
+def test_chain_rhf_full_device_scf_matches_oracle(n):
+    """BASELINE config 2 in miniature: synthetic chain RHF, complete SCF loop with DIIS on
+    the device, ERI generated in HBM."""
+    model = scf_b200.synthetic.ChainModel(n)
+    builder = scf_b200.JKBuilderCUDA.synthetic(n, "chain", 0, aux=model.aux)
+    problem = scf_b200.ScfProblem(model.overlap, model.n_elec(), n, True,
+                                  {"nuclear_repulsion": model.nuclear_repulsion},
+                                  {"kinetic": model.kinetic, "nuclear_attraction": model.nuclear_attraction},
+                                  {"coulomb+exchange": builder})
+    kw = dict(max_error_norm=1e-9, max_energy_total_change=1e-11, max_iter=200)
+    res = scf_b200.run_scf(problem, scf_b200.compute_guess(problem), verbose=False, **kw)
+    x, s, t, v, enn = synth.chain_matrices(n)
+    op = o.ScfProblem(s, (n // 2, n // 2), n, True, {"nuclear_repulsion": enn},
+                      {"kinetic": t, "nuclear_attraction": v},
+                      {"coulomb+exchange": o.JKBuilderFromTensor(synth.chain_eri(n))})
+    ref = o.run_scf(op, o.compute_guess_hcore(op), **kw)
+    assert res["converged"] and ref["converged"] and res["mode"] == "device"
+    assert abs(res["energies_newest"]["total"] - ref["energies_newest"]["total"]) < 1e-10
+    builder.close()
+
+
+def test_termwise_energies_match_oracle(golden_dir):
+    problem, _ = cuda_problem(golden_dir, "integrals_c_3-21g", False)
+    op, integrals = oracle_problem(golden_dir, "integrals_c_3-21g", False)
+    res = scf_b200.run_scf(problem, scf_b200.compute_guess(problem), verbose=False)
+    en = S.compute_termwise_hf_energies(res, problem)
+    ej, ek = o.termwise_jk_energies(integrals["electron_repulsion_bbbb"], res["density"])
+    assert abs(en["coulomb"] - ej) < 1e-11 and abs(en["exchange"] - ek) < 1e-11
+    assert abs(en["coulomb"] + en["exchange"] - en["2e"]) < 1e-6      # stale iterate vs its density
