@@ -110,3 +110,32 @@ def hash_eri_elements(a, b, c, d, seed=SEED_ERI):
     p1, p2 = _pair(a, b), _pair(c, d)
     p, q = np.maximum(p1, p2), np.minimum(p1, p2)
     return _uniform_pm1(p * (p + np.uint64(1)) // np.uint64(2) + q, seed)
+
+
+def random_symmetric_eri(n, rng):
+    """Random tensor with the full 8-fold permutational symmetry (ij|kl) = (ji|kl) = (ij|lk)
+    = (kl|ij) (test input for the packed layout)."""
+    t = rng.standard_normal((n, n, n, n))
+    t = t + t.transpose(1, 0, 2, 3)
+    t = t + t.transpose(0, 1, 3, 2)
+    t = t + t.transpose(2, 3, 0, 1)
+    return np.asfortranarray(t / 8)
+
+
+def pack8(eri):
+    """Oracle statement of the packed8 storage: row p = pr(i,j) (i >= j) holds
+    q = pr(k,l) <= p; value (ij|kl) * 0.5^{[i=j]+[k=l]+[p=q]}."""
+    n = eri.shape[0]
+    out = []
+    for i in range(n):
+        for j in range(i + 1):
+            p = i * (i + 1) // 2 + j
+            for k in range(i + 1):
+                for l in range(k + 1):
+                    q = k * (k + 1) // 2 + l
+                    if q > p:
+                        break
+                    v = eri[i, j, k, l]
+                    v *= 0.5 ** ((i == j) + (k == l) + (p == q))
+                    out.append(v)
+    return np.array(out)

@@ -128,9 +128,16 @@ class JKBuilderCUDA(TwoElectronBuilder):
 
     def eri_shard(self):
         """Owned nu-slabs copied back to the host, shape (n,n,n,hi-lo) (small n only)."""
+        assert self.layout == "full", "use eri_shard_raw() for the packed layout"
         lo, hi = self.shard_range
         n = self.n_bas
         buf = np.empty((n, n, n, hi - lo), order="F")
+        capi.check(capi.lib().scfb_eri_download(self._h, capi.ptr(buf)), self._h)
+        return buf
+
+    def eri_shard_raw(self):
+        """The shard exactly as stored in HBM, flat (packed8: pre-scaled packed rows)."""
+        buf = np.empty(self.eri_bytes // 8)
         capi.check(capi.lib().scfb_eri_download(self._h, capi.ptr(buf)), self._h)
         return buf
 

@@ -265,6 +265,7 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
   const int n = h->n;
   const int n_slabs = h->nu_hi - h->nu_lo;
   if (n_slabs <= 0) {  // this rank owns nothing: its partial stays zero
+    if (h->timed) cudaEventRecord(h->ev[3], h->stream);
     if (h->timed) cudaEventRecord(h->ev[1], h->stream);
     return SCFB_OK;
   }
@@ -272,6 +273,7 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
   // VEC=2 needs R = n/2 <= MAX_THREADS; wider rows fall back to more rows per thread? no:
   // rows longer than 2*MAX_THREADS are rejected at create time.
   cudaError_t e;
+  if (h->timed) cudaEventRecord(h->ev[3], h->stream);
   if (even)
     e = n_spin == 1 ? launch_stream<2, 1>(h, d_density, d_total)
                     : launch_stream<2, 2>(h, d_density, d_total);

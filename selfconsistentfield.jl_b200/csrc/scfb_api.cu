@@ -1,6 +1,7 @@
 // C-ABI entry points of libscf_b200.so (declared in include/scf_b200.h): lifecycle, ERI
 // storage and the host/device-pointer Fock-build calls.  No CPU fallback anywhere: every
 // compute entry point needs a CUDA device and fails with SCFB_ERR_CUDA otherwise.
+#include <cstdlib>
 #include <new>
 
 #include "scfb_internal.h"
@@ -43,6 +44,11 @@ int check_build_args(scfb_handle_s* h, int n_spin, const void* a, const void* b,
   return SCFB_OK;
 }
 
+int launch_jk(scfb_handle_s* h, int n_spin, const double* d_density, const double* d_total) {
+  return h->layout == SCFB_LAYOUT_FULL ? scfb_launch_jk_full(h, n_spin, d_density, d_total)
+                                       : scfb_launch_jk_packed(h, n_spin, d_density, d_total);
+}
+
 }  // namespace
 
 extern "C" {
@@ -59,9 +65,11 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
                "unknown layout %d", layout);
   SCFB_REQUIRE(nullptr, n_ranks >= 1 && rank >= 0 && rank < n_ranks, "bad rank %d of %d", rank,
                n_ranks);
-  SCFB_REQUIRE(nullptr, (n_bas % 2 == 0 && n_bas <= 512) || (n_bas % 2 == 1 && n_bas <= 255),
-               "n_bas=%d unsupported: even n <= 512 or odd n <= 255", n_bas);
-  SCFB_REQUIRE(nullptr, layout == SCFB_LAYOUT_FULL, "packed8 layout not built yet");
+  if (layout == SCFB_LAYOUT_FULL)
+    SCFB_REQUIRE(nullptr, (n_bas % 2 == 0 && n_bas <= 512) || (n_bas % 2 == 1 && n_bas <= 255),
+                 "n_bas=%d unsupported by the full layout: even n <= 512 or odd n <= 255", n_bas);
+  else
+    SCFB_REQUIRE(nullptr, n_bas <= 512, "n_bas=%d unsupported by the packed8 layout: n <= 512", n_bas);
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
   if (e != cudaSuccess || n_dev == 0)
@@ -77,10 +85,16 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
   h->device = device;
   h->rank = rank;
   h->n_ranks = n_ranks;
-  scfb_split_range(n_bas, rank, n_ranks, &h->nu_lo, &h->nu_hi);
   const uint64_t n = n_bas, n2 = n * n;
-  h->eri_elems = n2 * n * (uint64_t)(h->nu_hi - h->nu_lo);
-  h->kpart_elems = scfb_kpart_elems_full(n_bas, h->nu_hi - h->nu_lo);
+  if (layout == SCFB_LAYOUT_FULL) {
+    scfb_split_range(n_bas, rank, n_ranks, &h->nu_lo, &h->nu_hi);
+    h->eri_elems = n2 * n * (uint64_t)(h->nu_hi - h->nu_lo);
+    h->kpart_elems = scfb_kpart_elems_full(n_bas, h->nu_hi - h->nu_lo);
+  } else {
+    scfb_packed_split(n_bas, rank, n_ranks, &h->i_lo, &h->i_hi);
+    h->pk_offset = scfb_packed_offset(h->i_lo);
+    h->eri_elems = scfb_packed_offset(h->i_hi) - h->pk_offset;
+  }
 
 #define CREATE_CUDA(call)                                                                   \
   do {                                                                                      \
@@ -106,6 +120,11 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
   h->jk_sum = h->jk;
   if (n_ranks > 1) CREATE_CUDA(cudaMalloc(&h->jk_sum, 3 * n2 * sizeof(double)));
   if (h->kpart_elems) CREATE_CUDA(cudaMalloc(&h->kpart, h->kpart_elems * sizeof(double)));
+  if (layout == SCFB_LAYOUT_PACKED8) {
+    const uint64_t P = n * (n + 1) / 2;
+    CREATE_CUDA(cudaMalloc(&h->pk_acc, (P + 2 * n2) * sizeof(double)));
+    CREATE_CUDA(cudaMalloc(&h->pk_dq2, P * sizeof(double)));
+  }
   CREATE_CUDA(cudaMallocHost(&h->h_stage, 5 * n2 * sizeof(double)));
   CREATE_CUDA(cudaStreamSynchronize(h->stream));
 #undef CREATE_CUDA
@@ -124,6 +143,8 @@ int scfb_destroy(scfb_handle_t h) {
   if (h->jk_sum != h->jk) cudaFree(h->jk_sum);
   cudaFree(h->jk);
   cudaFree(h->kpart);
+  cudaFree(h->pk_acc);
+  cudaFree(h->pk_dq2);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
@@ -149,8 +170,9 @@ int scfb_set_stream(scfb_handle_t h, void* cuda_stream) {
 
 int scfb_shard_range(scfb_handle_t h, int* nu_lo, int* nu_hi) {
   if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
-  if (nu_lo) *nu_lo = h->nu_lo;
-  if (nu_hi) *nu_hi = h->nu_hi;
+  const bool full = h->layout == SCFB_LAYOUT_FULL;
+  if (nu_lo) *nu_lo = full ? h->nu_lo : h->i_lo;
+  if (nu_hi) *nu_hi = full ? h->nu_hi : h->i_hi;
   return SCFB_OK;
 }
 
@@ -163,6 +185,7 @@ int scfb_eri_bytes(scfb_handle_t h, uint64_t* bytes) {
 int scfb_eri_upload_slabs(scfb_handle_t h, const double* host_slabs, int nu_first, int nu_count) {
   if (int rc = check_handle(h)) return rc;
   SCFB_REQUIRE(h, host_slabs, "null host pointer");
+  SCFB_REQUIRE(h, h->layout == SCFB_LAYOUT_FULL, "slab upload is for the full layout; use scfb_eri_upload");
   SCFB_REQUIRE(h, nu_first >= 0 && nu_count >= 0 && nu_first + nu_count <= h->n,
                "slab range [%d, %d) outside [0, %d)", nu_first, nu_first + nu_count, h->n);
   const int lo = nu_first > h->nu_lo ? nu_first : h->nu_lo;
@@ -180,6 +203,22 @@ int scfb_eri_upload_slabs(scfb_handle_t h, const double* host_slabs, int nu_firs
 }
 
 int scfb_eri_upload(scfb_handle_t h, const double* host_eri) {
+  if (h && h->layout == SCFB_LAYOUT_PACKED8) {
+    if (int rc = check_handle(h)) return rc;
+    SCFB_REQUIRE(h, host_eri, "null host pointer");
+    if (h->eri_elems) {
+      double* tmp = static_cast<double*>(std::malloc(h->eri_elems * sizeof(double)));
+      if (!tmp) return scfb_fail(h, SCFB_ERR_OOM, "host packing buffer allocation failed");
+      scfb_pack_host(host_eri, h->n, h->i_lo, h->i_hi, tmp);
+      cudaError_t e = cudaMemcpyAsync(h->eri, tmp, h->eri_elems * sizeof(double),
+                                      cudaMemcpyHostToDevice, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      std::free(tmp);
+      if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "packed upload: %s", cudaGetErrorString(e));
+    }
+    h->eri_ready = true;
+    return SCFB_OK;
+  }
   int rc = scfb_eri_upload_slabs(h, host_eri, 0, h ? h->n : 0);
   if (rc == SCFB_OK) h->eri_ready = true;
   return rc;
@@ -205,7 +244,8 @@ int scfb_eri_generate(scfb_handle_t h, int family, uint64_t seed, const double* 
       return scfb_fail(h, SCFB_ERR_CUDA, "aux upload: %s", cudaGetErrorString(e));
     }
   }
-  int rc = scfb_launch_generate_full(h, family, seed, d_aux);
+  int rc = h->layout == SCFB_LAYOUT_FULL ? scfb_launch_generate_full(h, family, seed, d_aux)
+                                         : scfb_launch_generate_packed(h, family, seed, d_aux);
   cudaError_t e = cudaStreamSynchronize(h->stream);
   if (d_aux) cudaFree(d_aux);
   if (rc) return rc;
@@ -216,7 +256,7 @@ int scfb_eri_generate(scfb_handle_t h, int family, uint64_t seed, const double* 
 
 int scfb_eri_download(scfb_handle_t h, double* host_shard) {
   if (int rc = check_handle(h)) return rc;
-  SCFB_REQUIRE(h, host_shard, "null host pointer");
+  SCFB_REQUIRE(h, host_shard, "null host pointer");  // packed: raw pre-scaled packed rows
   SCFB_CUDA(h, cudaMemcpyAsync(host_shard, h->eri, h->eri_elems * sizeof(double),
                                cudaMemcpyDeviceToHost, h->stream));
   SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -228,7 +268,7 @@ int scfb_fock_jk_dev(scfb_handle_t h, int n_spin, const double* d_density,
   if (int rc = check_handle(h)) return rc;
   if (int rc = check_build_args(h, n_spin, d_density, d_total_density, d_out)) return rc;
   if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
-  if (int rc = scfb_launch_jk_full(h, n_spin, d_density, d_total_density)) return rc;
+  if (int rc = launch_jk(h, n_spin, d_density, d_total_density)) return rc;
   const double* jk_final = h->jk;
   if (h->n_ranks > 1 && h->nccl_comm) {
     if (int rc = scfb_comm_allreduce_jk(h, n_spin)) return rc;
@@ -260,7 +300,7 @@ int scfb_jk_split(scfb_handle_t h, int n_spin, const double* density, const doub
   SCFB_REQUIRE(h, K, "null K pointer");
   if (int rc = stage_inputs(h, n_spin, density, total_density, nullptr)) return rc;
   if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
-  if (int rc = scfb_launch_jk_full(h, n_spin, h->d_density, h->d_total)) return rc;
+  if (int rc = launch_jk(h, n_spin, h->d_density, h->d_total)) return rc;
   const double* jk_final = h->jk;
   if (h->n_ranks > 1 && h->nccl_comm) {
     if (int rc = scfb_comm_allreduce_jk(h, n_spin)) return rc;
@@ -280,7 +320,7 @@ int scfb_last_build_ms(scfb_handle_t h, double* stream_ms, double* total_ms) {
   if (int rc = check_handle(h)) return rc;
   SCFB_CUDA(h, cudaEventSynchronize(h->ev[2]));
   float a = 0.f, b = 0.f;
-  SCFB_CUDA(h, cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+  SCFB_CUDA(h, cudaEventElapsedTime(&a, h->ev[3], h->ev[1]));
   SCFB_CUDA(h, cudaEventElapsedTime(&b, h->ev[0], h->ev[2]));
   if (stream_ms) *stream_ms = a;
   if (total_ms) *total_ms = b;

@@ -18,8 +18,11 @@ struct scfb_handle_s {
   int device = 0;
   int rank = 0, n_ranks = 1;
   int nu_lo = 0, nu_hi = 0;  // owned nu-slabs (full layout) — [lo, hi)
-  // packed layout: owned rows [row_lo, row_hi) of the lower-triangular P x P pair matrix
-  int64_t row_lo = 0, row_hi = 0;
+  // packed layout: owned first-index blocks i in [i_lo, i_hi) (all rows pr(i,j), j <= i)
+  int i_lo = 0, i_hi = 0;
+  uint64_t pk_offset = 0;       // packed elements stored before this shard
+  double* pk_acc = nullptr;     // [J~ (P) | K' (2 n^2)] fp64 RED accumulators
+  double* pk_dq2 = nullptr;     // packed 2*Dtot (P)
 
   double* eri = nullptr;  // device shard
   uint64_t eri_elems = 0;
@@ -88,6 +91,12 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
                         const double* d_total);            // fills h->jk for owned columns
 int scfb_launch_accumulate(scfb_handle_s* h, int n_spin, const double* d_jk, double* d_out);  // out += J - K_s
 uint64_t scfb_kpart_elems_full(int n, int n_slabs);
+// jk_packed.cu
+void scfb_packed_split(int n, int rank, int n_ranks, int* i_lo, int* i_hi);
+uint64_t scfb_packed_offset(int i);
+int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density, const double* d_total);
+int scfb_launch_generate_packed(scfb_handle_s* h, int family, uint64_t seed, const double* d_aux);
+void scfb_pack_host(const double* full, int n, int i_lo, int i_hi, double* out);
 // eri_gen.cu
 int scfb_launch_generate_full(scfb_handle_s* h, int family, uint64_t seed, const double* d_aux);
 // comm.cu
