@@ -10,7 +10,7 @@
 // equals  J_ab = sum_cd (ab|cd) Dtot_cd,  K_ac = sum_bd (ab|cd) D_bd.
 //
 // Per stored element (i,j,k,l; f), with Dq2 = 2*Dtot in pair space:
-//   J~[p] += f Dq2[q]          J~[q] += f Dq2[p]                      (J_ij = J_ji = J~[pr(i,j)])
+//   J~[p] += f Dq2[q]          J~[q] += f Dq2[p]       (J_ij = J_ji = J~[pr(i,j)], J_ii = 2 J~[pr(i,i)])
 //   K'[i,k] += f D[j,l]   K'[i,l] += f D[j,k]   K'[j,k] += f D[i,l]   K'[j,l] += f D[i,k]
 // and K = K' + K'^T.  2 + 4 n_spin FMAs per 8 bytes: still HBM-bound (1.5-2.5 flop/B).
 //
@@ -202,7 +202,8 @@ __global__ void unpack_jk_kernel(const double* __restrict__ Jp, const double* __
        e += (size_t)gridDim.x * blockDim.x) {
     const size_t a = e % n, b = e / n;
     const size_t hi = a > b ? a : b, lo = a > b ? b : a;
-    jk[e] = Jp[tri(hi) + lo];
+    // a diagonal pair (a,a) is the target of both the (ab|..) and (ba|..) permutations
+    jk[e] = (a == b ? 2.0 : 1.0) * Jp[tri(hi) + lo];
     for (int s = 0; s < n_spin; ++s) jk[(1 + s) * n2 + e] = Kp[s * n2 + e] + Kp[s * n2 + b + n * a];
   }
 }
