@@ -46,9 +46,17 @@ def parse():
     return p.parse_args()
 
 
+def eri_total_bytes(a):
+    if a.layout == "full":
+        return 8 * a.n_bas ** 4
+    p = a.n_bas * (a.n_bas + 1) // 2
+    return 8 * (p * (p + 1) // 2)
+
+
 def workload_name(a):
     spin = "UHF" if a.n_spin == 2 else "RHF"
-    return f"synthetic {spin} n_bf={a.n_bas}, {a.layout} fp64 ERI ({8 * a.n_bas ** 4 / 1e9:.2f} GB), hash family"
+    return (f"synthetic {spin} n_bf={a.n_bas}, {a.layout} fp64 ERI "
+            f"({eri_total_bytes(a) / 1e9:.2f} GB), hash family")
 
 
 def peaks():
@@ -164,6 +172,25 @@ def run_reference(a, rank):
     print(json.dumps(line), flush=True)
 
 
+def verify_known_answer(builder, n, n_spin):
+    """Cheap exactness check of the timed builder (every rank): symmetric unit densities pick
+    single tensor elements of the hash family, whose values are O(1) closed forms."""
+    from scf_b200 import synthetic
+    a0, b0, a1, b1 = 3 % n, (n - 5) % n, (n // 2) % n, 1 % n
+    unit = lambda a, b: synthetic.unit_symmetric(n, a, b)
+    dens = np.stack([unit(a1, b1)] * n_spin, axis=2)
+    j, k = builder.jk(dens, unit(a0, b0))
+    idx = np.arange(n)
+    e = lambda a, b, c, d: synthetic.hash_eri_elements(a, b, c, d)
+    w0 = 1.0 if a0 == b0 else 2.0        # E_ab + E_ba picks eri[a,b,..] + eri[b,a,..]
+    jr = w0 * e(a0, b0, idx[:, None], idx[None, :])
+    kr = e(idx[:, None], b1, a1, idx[None, :]) + (0 if a1 == b1 else e(idx[:, None], a1, b1, idx[None, :]))
+    ok = np.abs(j - jr).max() <= 1e-13 * np.abs(jr).max() and np.abs(k[:, :, 0] - kr).max() <= 1e-13 * np.abs(kr).max()
+    if not ok:
+        raise SystemExit("bench.py: verification of the timed builder FAILED")
+    return "unit-density known answers match the closed-form tensor elements"
+
+
 # ---- ours ---------------------------------------------------------------------------------
 def run_ours(a, rank, local_rank, world):
     import torch
@@ -246,6 +273,7 @@ def run_ours(a, rank, local_rank, world):
         e2e_s = time.perf_counter() - t0
         t_load2 = time.perf_counter()
     clocks = sampler.stop(t_load0, t_load2) if sampler else None
+    verified = verify_known_answer(builder, n, n_spin)
 
     if dist is not None:
         t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
@@ -254,8 +282,10 @@ def run_ours(a, rank, local_rank, world):
 
     if rank == 0:
         peak, peak_src = peaks()
-        lo, hi = builder.shard_range
-        launch_bytes = 8.0 * n ** 3 * (hi - lo)             # algorithmic bytes of one stream launch
+        # algorithmic bytes of one stream launch = this rank's share of the UNPADDED tensor
+        launch_bytes = float(builder.eri_bytes)
+        if a.layout == "packed8":
+            launch_bytes *= eri_total_bytes(a) / (8.0 * synthetic.packed8_total(n))
         k_ms = float(np.mean(stream_ms))
         achieved = launch_bytes / (k_ms * 1e-3) / 1e9
         line = {
@@ -264,17 +294,18 @@ def run_ours(a, rank, local_rank, world):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(a), "n_bas": n, "n_spin": n_spin,
-                       "layout": a.layout, "sharding": f"nu-slabs over {world} rank(s)",
+                       "layout": a.layout, "sharding": f"{'nu-slabs' if a.layout == 'full' else 'i-blocks'} over {world} rank(s)",
                        "l2_policy": "inputs (ERI shard) far larger than the 126 MB L2; no flush"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None,
-                         "kernel": "jk_full_stream_kernel", "kernel_ms": k_ms,
+                         "kernel": "jk_full_stream_kernel" if a.layout == "full" else "jk_packed_kernel",
+                         "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": launch_bytes, "peak_source": peak_src,
                          "kernel_share_of_step": k_ms / (ms / a.steps)},
             "e2e": {"value": e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": 8 * n2 * (2 * n_spin + 1),
                     "d2h_bytes_per_step": 8 * n2 * n_spin, "steps": e2e_steps},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "verified": verified,
             "clocks": clocks,
         }
         if world == 1 and not a.no_cpu_baseline:

@@ -122,20 +122,30 @@ def random_symmetric_eri(n, rng):
     return np.asfortranarray(t / 8)
 
 
-def pack8(eri):
-    """Oracle statement of the packed8 storage: row p = pr(i,j) (i >= j) holds
-    q = pr(k,l) <= p; value (ij|kl) * 0.5^{[i=j]+[k=l]+[p=q]}."""
+def packed8_seg_off(k):
+    """Padded elements of the k-segments 0..k-1 of a packed row (each padded to even length)."""
+    return k * (k + 1) // 2 + (k + 1) // 2
+
+
+def packed8_total(n):
+    """Stored (padded) elements of the packed8 layout = B[n] of DESIGN.md."""
+    return sum((i + 1) * packed8_seg_off(i) + packed8_seg_off(i + 1) for i in range(n))
+
+
+def pack8(eri, i_lo=0, i_hi=None):
+    """Oracle statement of the packed8 storage: for i >= j the row (i,j) holds the
+    segments k = 0..i with l = 0..k (k < i) or l = 0..j (k == i), each padded with one zero to
+    even length; value (ij|kl) * 0.5^{[i=j]+[k=l]+[pr(i,j)=pr(k,l)]}."""
     n = eri.shape[0]
+    i_hi = n if i_hi is None else i_hi
     out = []
-    for i in range(n):
+    for i in range(i_lo, i_hi):
         for j in range(i + 1):
-            p = i * (i + 1) // 2 + j
             for k in range(i + 1):
-                for l in range(k + 1):
-                    q = k * (k + 1) // 2 + l
-                    if q > p:
-                        break
-                    v = eri[i, j, k, l]
-                    v *= 0.5 ** ((i == j) + (k == l) + (p == q))
+                lmax = k if k < i else j
+                for l in range(lmax + 1):
+                    v = eri[i, j, k, l] * 0.5 ** ((i == j) + (k == l) + (i == k and j == l))
                     out.append(v)
+                if (lmax + 1) % 2:
+                    out.append(0.0)
     return np.array(out)

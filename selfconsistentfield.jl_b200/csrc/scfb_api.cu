@@ -69,7 +69,7 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
     SCFB_REQUIRE(nullptr, (n_bas % 2 == 0 && n_bas <= 512) || (n_bas % 2 == 1 && n_bas <= 255),
                  "n_bas=%d unsupported by the full layout: even n <= 512 or odd n <= 255", n_bas);
   else
-    SCFB_REQUIRE(nullptr, n_bas <= 512, "n_bas=%d unsupported by the packed8 layout: n <= 512", n_bas);
+    SCFB_REQUIRE(nullptr, n_bas <= 2048, "n_bas=%d unsupported by the packed8 layout: n <= 2048", n_bas);
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
   if (e != cudaSuccess || n_dev == 0)
@@ -121,9 +121,13 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
   if (n_ranks > 1) CREATE_CUDA(cudaMalloc(&h->jk_sum, 3 * n2 * sizeof(double)));
   if (h->kpart_elems) CREATE_CUDA(cudaMalloc(&h->kpart, h->kpart_elems * sizeof(double)));
   if (layout == SCFB_LAYOUT_PACKED8) {
-    const uint64_t P = n * (n + 1) / 2;
-    CREATE_CUDA(cudaMalloc(&h->pk_acc, (P + 2 * n2) * sizeof(double)));
-    CREATE_CUDA(cudaMalloc(&h->pk_dq2, P * sizeof(double)));
+    const uint64_t PQ = scfb_packed_dq_elems(n_bas);
+    CREATE_CUDA(cudaMalloc(&h->pk_acc, (PQ + 2 * n2) * sizeof(double)));
+    CREATE_CUDA(cudaMalloc(&h->pk_dq2, PQ * sizeof(double)));
+    if (int rc_ = scfb_packed_upload_table(h)) {
+      scfb_destroy(h);
+      return rc_;
+    }
   }
   CREATE_CUDA(cudaMallocHost(&h->h_stage, 5 * n2 * sizeof(double)));
   CREATE_CUDA(cudaStreamSynchronize(h->stream));
@@ -145,6 +149,7 @@ int scfb_destroy(scfb_handle_t h) {
   cudaFree(h->kpart);
   cudaFree(h->pk_acc);
   cudaFree(h->pk_dq2);
+  cudaFree(h->pk_btab);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);

@@ -22,7 +22,8 @@ struct scfb_handle_s {
   int i_lo = 0, i_hi = 0;
   uint64_t pk_offset = 0;       // packed elements stored before this shard
   double* pk_acc = nullptr;     // [J~ (P) | K' (2 n^2)] fp64 RED accumulators
-  double* pk_dq2 = nullptr;     // packed 2*Dtot (P)
+  double* pk_dq2 = nullptr;     // 2*Dtot in (padded) pair space
+  uint64_t* pk_btab = nullptr;  // B[i]: offset of row (i,0), n+1 entries
 
   double* eri = nullptr;  // device shard
   uint64_t eri_elems = 0;
@@ -94,6 +95,8 @@ uint64_t scfb_kpart_elems_full(int n, int n_slabs);
 // jk_packed.cu
 void scfb_packed_split(int n, int rank, int n_ranks, int* i_lo, int* i_hi);
 uint64_t scfb_packed_offset(int i);
+uint64_t scfb_packed_dq_elems(int n);
+int scfb_packed_upload_table(scfb_handle_s* h);
 int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density, const double* d_total);
 int scfb_launch_generate_packed(scfb_handle_s* h, int family, uint64_t seed, const double* d_aux);
 void scfb_pack_host(const double* full, int n, int i_lo, int i_hi, double* out);

@@ -34,6 +34,34 @@ def hash_density(n: int, seed: int) -> np.ndarray:
     return np.asfortranarray(_splitmix_uniform(hi * (hi + np.uint64(1)) // np.uint64(2) + lo, seed))
 
 
+def packed8_total(n: int) -> int:
+    """Stored (padded) elements of the packed8 layout (csrc/jk_packed.cu: B[n])."""
+    seg = lambda k: k * (k + 1) // 2 + (k + 1) // 2
+    return sum((i + 1) * seg(i) + seg(i + 1) for i in range(n))
+
+
+def unit_symmetric(n: int, a: int, b: int) -> np.ndarray:
+    """E_ab + E_ba (or E_aa): the symmetric density that picks single tensor elements."""
+    m = np.zeros((n, n), order="F")
+    m[a, b] = 1.0
+    m[b, a] = 1.0
+    return m
+
+
+def hash_eri_elements(a, b, c, d, seed: int = SEED_ERI) -> np.ndarray:
+    """eri[a,b,c,d] of the HASH family for broadcastable index arrays (closed form, O(1))."""
+    a, b, c, d = (np.asarray(v, dtype=np.uint64) for v in (a, b, c, d))
+    one, two = np.uint64(1), np.uint64(2)
+
+    def pair(i, j):
+        hi, lo = np.maximum(i, j), np.minimum(i, j)
+        return hi * (hi + one) // two + lo
+
+    p1, p2 = pair(a, b), pair(c, d)
+    p, q = np.maximum(p1, p2), np.minimum(p1, p2)
+    return _splitmix_uniform(p * (p + one) // two + q, seed)
+
+
 class ChainModel:
     """x, S, T, V, E_nn of the chain family plus the aux array for the device generator."""
 

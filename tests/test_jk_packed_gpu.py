@@ -28,7 +28,7 @@ def test_packed_matches_oracle_random_symmetric(n, n_spin):
     density = np.stack([sym(rng, n) for _ in range(n_spin)], axis=2)
     total = sym(rng, n)                       # caller-supplied, symmetric
     b = scf_b200.JKBuilderCUDA.from_tensor(eri, layout="packed8")
-    assert b.eri_bytes == 8 * (n * (n + 1) // 2) * (n * (n + 1) // 2 + 1) // 2
+    assert b.eri_bytes == 8 * synth.packed8_total(n)
     j, k = b.jk(density, total)
     jr, kr = o.jk_exact(eri, density, total)
     assert rel_err(j, jr) < RTOL
@@ -91,8 +91,7 @@ def test_packed_shard_partials_sum_to_full(n, n_ranks):
         part.close()
     assert bounds[0][0] == 0 and bounds[-1][1] == n
     assert all(bounds[g][1] == bounds[g + 1][0] for g in range(n_ranks - 1))
-    p = n * (n + 1) // 2
-    assert nbytes == 8 * p * (p + 1) // 2
+    assert nbytes == 8 * synth.packed8_total(n)
     assert rel_err(js, jr) < RTOL and rel_err(ks, kr) < RTOL
 
 
