@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscf_b200.so")
+# SCFB_LIB overrides the library path (kernel experiments only)
+LIB_PATH = os.environ.get("SCFB_LIB") or os.path.join(_HERE, "libscf_b200.so")
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_CUSOLVER, ERR_NCCL, ERR_OOM, ERR_STATE = -1, -2, -3, -4, -5, -6

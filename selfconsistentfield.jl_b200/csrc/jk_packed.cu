@@ -29,11 +29,11 @@
 // the 1e-12 relative gate).
 #include "scfb_internal.h"
 
+#include <cstdlib>
 #include <vector>
 
 namespace {
 
-constexpr int KC = 8;    // k values per work item
 constexpr int LB = 128;  // threads per CTA = 4 independent warps, 256 l values
 
 __host__ __device__ __forceinline__ uint64_t tri(uint64_t i) { return i * (i + 1) / 2; }
@@ -45,37 +45,59 @@ __device__ __forceinline__ double2 ldg_stream2(const double* p) {
   return r;
 }
 
-// Sum 8 per-lane values over the 32 lanes of a warp with 9 (instead of 40) shuffles.
-// On return lanes with (lane & 3) == 0 hold the total of value index
-// 4*bit4 + 2*bit3 + bit2 of their lane id.
-__device__ __forceinline__ double warp_transpose_reduce8(const double (&v)[8], int lane) {
+// Sum V (4 or 8) per-lane values over the 32 lanes of a warp with V+1 (instead of 5V)
+// shuffles: each butterfly stage halves the number of values a lane still carries.
+// On return lanes with (lane % (32/V)) == 0 hold the total of value index lane / (32/V)
+// in bit-reversed-free order given by transpose_reduce_index<V>().
+template <int V>
+__device__ __forceinline__ double warp_transpose_reduce(const double (&v)[V], int lane) {
+  static_assert(V == 8 || V == 4, "V must be 4 or 8");
   double a[4], b[2], c;
-  const bool hi16 = lane & 16;
+  if (V == 8) {
+    const bool hi16 = lane & 16;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const double keep = hi16 ? v[t + 4] : v[t];
-    const double send = hi16 ? v[t] : v[t + 4];
-    a[t] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-  const bool hi8 = lane & 8;
+    for (int t = 0; t < 4; ++t) {
+      const double keep = hi16 ? v[(t + 4) % V] : v[t];
+      const double send = hi16 ? v[t] : v[(t + 4) % V];
+      a[t] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    const bool hi8 = lane & 8;
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const double keep = hi8 ? a[t + 2] : a[t];
-    const double send = hi8 ? a[t] : a[t + 2];
-    b[t] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-  const bool hi4 = lane & 4;
-  {
+    for (int t = 0; t < 2; ++t) {
+      const double keep = hi8 ? a[t + 2] : a[t];
+      const double send = hi8 ? a[t] : a[t + 2];
+      b[t] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const bool hi4 = lane & 4;
     const double keep = hi4 ? b[1] : b[0];
     const double send = hi4 ? b[0] : b[1];
     c = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  } else {
+    const bool hi16 = lane & 16;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const double keep = hi16 ? v[(t + 2) % V] : v[t];
+      const double send = hi16 ? v[t] : v[(t + 2) % V];
+      b[t] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    const bool hi8 = lane & 8;
+    const double keep = hi8 ? b[1] : b[0];
+    const double send = hi8 ? b[0] : b[1];
+    c = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
   }
   c += __shfl_xor_sync(0xffffffffu, c, 2);
   c += __shfl_xor_sync(0xffffffffu, c, 1);
   return c;
 }
-__device__ __forceinline__ int transpose_reduce8_index(int lane) {
-  return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+template <int V>
+__device__ __forceinline__ int transpose_reduce_index(int lane) {
+  return V == 8 ? ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)
+                : ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+}
+template <int V>
+__device__ __forceinline__ bool transpose_reduce_owner(int lane) {
+  return V == 8 ? (lane & 3) == 0 : (lane & 7) == 0;
 }
 
 __device__ __forceinline__ double warp_sum(double x) {
@@ -87,7 +109,7 @@ __device__ __forceinline__ double warp_sum(double x) {
 // One work item of one warp.  D: n x n x NSPIN symmetric; dq2: 2*Dtot in pair space, stored
 // with the SAME padded segment offsets seg_off(k)+l (pads zero).  Kp: n x n x NSPIN
 // accumulators; Jp: accumulators indexed like dq2.
-template <int NSPIN, bool DIAG>
+template <int NSPIN, int KC, bool DIAG>
 __device__ __forceinline__ void packed_item(const double* __restrict__ eri_i,  // row (i,0)
                                             const double* __restrict__ D,
                                             const double* __restrict__ dq2,
@@ -148,33 +170,27 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_i,  /
   // running warps do not all RED into the same K'[j,:] row at the same time.
   int j = (int)(rot % (uint32_t)rows);
   const double* row = eri_i + (uint64_t)j * Ei + seg_off(j);
-  double2 w[KC], wn[KC];
-  load_row(row, j, w);
-  for (int step = 0; step < rows; ++step) {
-    const int jn = j + 1 == rows ? 0 : j + 1;
-    // row (i,j+1) starts E(i) + ceil2(j+1) elements after row (i,j)
-    const double* row_n = jn ? row + Ei + ((j + 2) & ~1) : eri_i;
-    if (step + 1 < rows) load_row(row_n, jn, wn);  // next row in flight while this one is consumed
 
-    const double dp2 = __ldg(dq2 + Ei + j);
+  auto consume = [&](int jj, const double2 (&w)[KC]) {
+    const double dp2 = __ldg(dq2 + Ei + jj);
     double dj_l[NSPIN][2], dj_k[NSPIN][KC];
 #pragma unroll
     for (int s = 0; s < NSPIN; ++s) {
-      const double* dj = D + s * n2 + (size_t)j * n;
+      const double* dj = D + s * n2 + (size_t)jj * n;
       dj_l[s][0] = __ldg(dj + lc);
       dj_l[s][1] = l1_in ? __ldg(dj + lc + 1) : 0.0;
 #pragma unroll
       for (int t = 0; t < KC; ++t) dj_k[s][t] = __ldg(dj + min(k0 + t, i));
     }
-    double jp = 0.0;
+    double jp0 = 0.0, jp1 = 0.0;
     double y[NSPIN][KC], z[NSPIN][2];
 #pragma unroll
     for (int s = 0; s < NSPIN; ++s) z[s][0] = z[s][1] = 0.0;
 #pragma unroll
     for (int t = 0; t < KC; ++t) {
       const double w0 = w[t].x, w1 = w[t].y;
-      jp = fma(w0, dq[t][0], jp);
-      jp = fma(w1, dq[t][1], jp);
+      jp0 = fma(w0, dq[t][0], jp0);
+      jp1 = fma(w1, dq[t][1], jp1);
       jq[t][0] = fma(w0, dp2, jq[t][0]);
       jq[t][1] = fma(w1, dp2, jq[t][1]);
 #pragma unroll
@@ -190,22 +206,55 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_i,  /
     }
     // per-row outputs (K' entries are accumulated at whichever of (a,b)/(b,a) coalesces:
     // K = K' + K'^T does not care)
-    jp = warp_sum(jp);
-    if (lane == 0) atomicAdd(Jp + Ei + j, jp);
+#ifndef SCFB_EXP_NO_ROWRED
+    const double jp = warp_sum(jp0 + jp1);
+    if (lane == 0) atomicAdd(Jp + Ei + jj, jp);
+#else
+    a2[0][0] += jp0 + jp1;
+#endif
 #pragma unroll
     for (int s = 0; s < NSPIN; ++s) {
-      double* kj = Kp + s * n2 + (size_t)n * j;
+      double* kj = Kp + s * n2 + (size_t)n * jj;
+#ifndef SCFB_EXP_NO_Z
       if (l0_in) atomicAdd(kj + l0, z[s][0]);  // K'[j,l]
       if (l1_in) atomicAdd(kj + l0 + 1, z[s][1]);
-      const double r = warp_transpose_reduce8(y[s], lane);
-      const int t = transpose_reduce8_index(lane);
-      if ((lane & 3) == 0 && k0 + t <= i) atomicAdd(kj + k0 + t, r);  // K'[j,k]
-    }
+#else
+      a2[s][0] += z[s][0] + z[s][1];
+#endif
+#ifndef SCFB_EXP_NO_ROWRED
+      const double r = warp_transpose_reduce<KC>(y[s], lane);
+      const int t = transpose_reduce_index<KC>(lane);
+      if (transpose_reduce_owner<KC>(lane) && k0 + t <= i) atomicAdd(kj + k0 + t, r);  // K'[j,k]
+#else
 #pragma unroll
-    for (int t = 0; t < KC; ++t) w[t] = wn[t];
-    row = row_n;
+      for (int t = 0; t < KC; ++t) a2[s][1] += y[s][t];
+      (void)kj;
+#endif
+    }
+  };
+  // row (i,j+1) starts E(i) + ceil2(j+1) elements after row (i,j); wraps to row (i,0)
+  auto advance = [&]() {
+    const int jn = j + 1 == rows ? 0 : j + 1;
+    row = jn ? row + Ei + ((j + 2) & ~1) : eri_i;
     j = jn;
+  };
+
+  // software pipeline, two rows per trip: the loads of the next row are in flight while the
+  // current one is consumed; ping-pong buffers avoid register copies
+  double2 wa[KC], wb[KC];
+  load_row(row, j, wa);
+  int step = 0;
+  for (; step + 2 <= rows; step += 2) {
+    const int ja = j;
+    advance();
+    load_row(row, j, wb);
+    consume(ja, wa);
+    const int jb = j;
+    advance();
+    if (step + 2 < rows) load_row(row, j, wa);
+    consume(jb, wb);
   }
+  if (step < rows) consume(j, wa);
 
   // per-item outputs
 #pragma unroll
@@ -213,9 +262,9 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_i,  /
     double* ki = Kp + s * n2 + (size_t)n * i;
     if (l0_in) atomicAdd(ki + l0, a2[s][0]);  // K'[i,l]
     if (l1_in) atomicAdd(ki + l0 + 1, a2[s][1]);
-    const double r = warp_transpose_reduce8(a1[s], lane);
-    const int t = transpose_reduce8_index(lane);
-    if ((lane & 3) == 0 && k0 + t <= i) atomicAdd(ki + k0 + t, r);  // K'[i,k]
+    const double r = warp_transpose_reduce<KC>(a1[s], lane);
+    const int t = transpose_reduce_index<KC>(lane);
+    if (transpose_reduce_owner<KC>(lane) && k0 + t <= i) atomicAdd(ki + k0 + t, r);  // K'[i,k]
   }
 #pragma unroll
   for (int t = 0; t < KC; ++t)
@@ -226,8 +275,8 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_i,  /
 }
 
 // grid = (n_kchunks, n_i_owned, n_lblocks), block = LB threads = 4 independent warps.
-template <int NSPIN>
-__global__ void __launch_bounds__(LB, 2)
+template <int NSPIN, int KC, int MINB>
+__global__ void __launch_bounds__(LB, MINB)
 jk_packed_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Btab,
                  uint64_t shard_offset, const double* __restrict__ D,
                  const double* __restrict__ dq2, double* __restrict__ Kp, double* __restrict__ Jp,
@@ -244,9 +293,241 @@ jk_packed_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Bt
   const uint32_t rot =
       blockIdx.x * 40503u + blockIdx.z * 9973u + blockIdx.y * 17u + (threadIdx.x >> 5) * 7u;
   if (kmax < i)
-    packed_item<NSPIN, false>(eri_i, D, dq2, Kp, Jp, n, i, k0, l0, lane, rot);
+    packed_item<NSPIN, KC, false>(eri_i, D, dq2, Kp, Jp, n, i, k0, l0, lane, rot);
   else
-    packed_item<NSPIN, true>(eri_i, D, dq2, Kp, Jp, n, i, k0, l0, lane, rot);
+    packed_item<NSPIN, KC, true>(eri_i, D, dq2, Kp, Jp, n, i, k0, l0, lane, rot);
+}
+
+// ------------------------------------------------------------------------------------------
+// v3: the same item decomposition, but the ERI stream is decoupled from the math with the
+// Blackwell/Hopper async-copy machinery: one producer warp issues 1-D bulk copies
+// (cp.async.bulk -> SASS UBLKCP, the TMA engine) of each row's k-segments into a ring of
+// shared-memory stages guarded by mbarriers; four consumer warps pull their l-pairs out of
+// the ring with immediate-offset LDS.128.  The padded layout makes every copy 16-byte aligned
+// and a multiple of 16 bytes.  Consumers never wait on DRAM latency and carry no prefetch
+// registers; the producer keeps STAGES rows (STAGES * KC * 2 KB) in flight per CTA.
+// ------------------------------------------------------------------------------------------
+constexpr int CW = 4;            // consumer warps per CTA
+constexpr int LW = 2 * 32 * CW;  // l values per CTA = 256
+constexpr int STAGES = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// grid = (n_kchunks, n_i_owned, n_lblocks of LW); block = (CW + 1) warps.
+template <int NSPIN, int KC, int MINB>
+__global__ void __launch_bounds__(32 * (CW + 1), MINB)
+jk_packed_tma_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Btab,
+                     uint64_t shard_offset, const double* __restrict__ D,
+                     const double* __restrict__ dq2, double* __restrict__ Kp,
+                     double* __restrict__ Jp, int n, int i_lo) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* ring = reinterpret_cast<double*>(smem_raw);                       // [STAGES][KC][LW]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + STAGES * KC * LW);    // [STAGES]
+  uint64_t* empty = full + STAGES;                                          // [STAGES]
+
+  const int i = i_lo + blockIdx.y;
+  const int k0 = blockIdx.x * KC;
+  if (k0 > i) return;
+  const int lb = blockIdx.z * LW;  // first l of this CTA
+  const int kmax = min(k0 + KC - 1, i);
+  if (lb > kmax) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // consumer warps whose 64 l values start beyond kmax have nothing to do
+  const int live = min(CW, (kmax - lb) / 64 + 1);
+  const bool diag = kmax == i;
+  const int rows = i + 1;
+  const uint64_t Ei = seg_off(i);
+  const double* eri_i = eri + (Btab[i] - shard_offset);
+  const uint32_t rot = blockIdx.x * 40503u + blockIdx.z * 9973u + blockIdx.y * 17u;
+  const int j_first = (int)(rot % (uint32_t)rows);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, live);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == CW) {
+    // ===== producer: one lane feeds the ring =====
+    if (lane != 0) return;
+    int j = j_first;
+    const double* row = eri_i + (uint64_t)j * Ei + seg_off(j);
+    for (int step = 0; step < rows; ++step) {
+      const int s = step % STAGES;
+      mbar_wait(empty + s, ((step / STAGES) & 1) ^ 1);
+      uint32_t len[KC], total = 0;
+#pragma unroll
+      for (int t = 0; t < KC; ++t) {
+        const int k = k0 + t;
+        // stored (padded) length of segment k in row (i,j), clipped to this CTA's l window
+        int seg = k > i ? 0 : ((k < i ? k : j) + 2) & ~1;
+        seg = seg - lb;
+        len[t] = seg <= 0 ? 0u : (uint32_t)(seg < LW ? seg : LW);
+        total += len[t];
+      }
+      mbar_expect_tx(full + s, total * 8u);
+      double* dst = ring + (size_t)s * KC * LW;
+#pragma unroll
+      for (int t = 0; t < KC; ++t)
+        if (len[t]) bulk_g2s(dst + t * LW, row + seg_off(min(k0 + t, i)) + lb, len[t] * 8u, full + s);
+      const int jn = j + 1 == rows ? 0 : j + 1;
+      row = jn ? row + Ei + ((j + 2) & ~1) : eri_i;
+      j = jn;
+    }
+    return;
+  }
+  if (warp >= live) return;
+
+  // ===== consumers =====
+  const size_t n2 = (size_t)n * n;
+  const int m = warp * 32 + lane;          // l-pair within the CTA window
+  const int l0 = lb + 2 * m;
+  const bool l0_in = l0 <= kmax, l1_in = l0 + 1 <= kmax;
+  const int lc = l0_in ? l0 : 0;
+
+  double di_l[NSPIN][2], di_k[NSPIN][KC], dq[KC][2];
+  bool ok[KC];
+  uint32_t joff[KC];
+#pragma unroll
+  for (int s = 0; s < NSPIN; ++s) {
+    const double* di = D + s * n2 + (size_t)i * n;
+    di_l[s][0] = __ldg(di + lc);
+    di_l[s][1] = l1_in ? __ldg(di + lc + 1) : 0.0;
+  }
+#pragma unroll
+  for (int t = 0; t < KC; ++t) {
+    const int k = k0 + t;
+    ok[t] = k <= i && l0 <= k;
+    const int kc = k <= i ? k : i;
+    joff[t] = (uint32_t)seg_off(kc) + (uint32_t)lc;
+    const double2 q2 =
+        ok[t] ? __ldg(reinterpret_cast<const double2*>(dq2 + joff[t])) : make_double2(0.0, 0.0);
+    dq[t][0] = q2.x;
+    dq[t][1] = q2.y;
+#pragma unroll
+    for (int s = 0; s < NSPIN; ++s) di_k[s][t] = __ldg(D + s * n2 + (size_t)i * n + kc);
+  }
+  double a1[NSPIN][KC], a2[NSPIN][2], jq[KC][2];
+#pragma unroll
+  for (int t = 0; t < KC; ++t) {
+    jq[t][0] = jq[t][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < NSPIN; ++s) a1[s][t] = 0.0;
+  }
+#pragma unroll
+  for (int s = 0; s < NSPIN; ++s) a2[s][0] = a2[s][1] = 0.0;
+
+  const double2* my = reinterpret_cast<const double2*>(ring) + m;  // + s*KC*LW/2 + t*LW/2
+  int j = j_first;
+  for (int step = 0; step < rows; ++step) {
+    const int s = step % STAGES;
+    mbar_wait(full + s, (step / STAGES) & 1);
+    double2 w[KC];
+#pragma unroll
+    for (int t = 0; t < KC; ++t) {
+      const double2 v = my[(s * KC + t) * (LW / 2)];
+      // stale ring contents beyond the copied length are masked here
+      const bool valid = ok[t] && (!diag || k0 + t < i || l0 <= j);
+      w[t] = valid ? v : make_double2(0.0, 0.0);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);  // stage is in registers: hand it back
+
+    const double dp2 = __ldg(dq2 + Ei + j);
+    double dj_l[NSPIN][2], dj_k[NSPIN][KC];
+#pragma unroll
+    for (int sp = 0; sp < NSPIN; ++sp) {
+      const double* dj = D + sp * n2 + (size_t)j * n;
+      dj_l[sp][0] = __ldg(dj + lc);
+      dj_l[sp][1] = l1_in ? __ldg(dj + lc + 1) : 0.0;
+#pragma unroll
+      for (int t = 0; t < KC; ++t) dj_k[sp][t] = __ldg(dj + min(k0 + t, i));
+    }
+    double jp0 = 0.0, jp1 = 0.0;
+    double y[NSPIN][KC], z[NSPIN][2];
+#pragma unroll
+    for (int sp = 0; sp < NSPIN; ++sp) z[sp][0] = z[sp][1] = 0.0;
+#pragma unroll
+    for (int t = 0; t < KC; ++t) {
+      const double w0 = w[t].x, w1 = w[t].y;
+      jp0 = fma(w0, dq[t][0], jp0);
+      jp1 = fma(w1, dq[t][1], jp1);
+      jq[t][0] = fma(w0, dp2, jq[t][0]);
+      jq[t][1] = fma(w1, dp2, jq[t][1]);
+#pragma unroll
+      for (int sp = 0; sp < NSPIN; ++sp) {
+        a1[sp][t] = fma(w0, dj_l[sp][0], a1[sp][t]);
+        a1[sp][t] = fma(w1, dj_l[sp][1], a1[sp][t]);
+        a2[sp][0] = fma(w0, dj_k[sp][t], a2[sp][0]);
+        a2[sp][1] = fma(w1, dj_k[sp][t], a2[sp][1]);
+        y[sp][t] = fma(w1, di_l[sp][1], w0 * di_l[sp][0]);
+        z[sp][0] = fma(w0, di_k[sp][t], z[sp][0]);
+        z[sp][1] = fma(w1, di_k[sp][t], z[sp][1]);
+      }
+    }
+    const double jp = warp_sum(jp0 + jp1);
+    if (lane == 0) atomicAdd(Jp + Ei + j, jp);
+#pragma unroll
+    for (int sp = 0; sp < NSPIN; ++sp) {
+      double* kj = Kp + sp * n2 + (size_t)n * j;
+      if (l0_in) atomicAdd(kj + l0, z[sp][0]);  // K'[j,l]
+      if (l1_in) atomicAdd(kj + l0 + 1, z[sp][1]);
+      const double r = warp_transpose_reduce<KC>(y[sp], lane);
+      const int t = transpose_reduce_index<KC>(lane);
+      if (transpose_reduce_owner<KC>(lane) && k0 + t <= i) atomicAdd(kj + k0 + t, r);  // K'[j,k]
+    }
+    j = j + 1 == rows ? 0 : j + 1;
+  }
+
+#pragma unroll
+  for (int sp = 0; sp < NSPIN; ++sp) {
+    double* ki = Kp + sp * n2 + (size_t)n * i;
+    if (l0_in) atomicAdd(ki + l0, a2[sp][0]);  // K'[i,l]
+    if (l1_in) atomicAdd(ki + l0 + 1, a2[sp][1]);
+    const double r = warp_transpose_reduce<KC>(a1[sp], lane);
+    const int t = transpose_reduce_index<KC>(lane);
+    if (transpose_reduce_owner<KC>(lane) && k0 + t <= i) atomicAdd(ki + k0 + t, r);  // K'[i,k]
+  }
+#pragma unroll
+  for (int t = 0; t < KC; ++t)
+    if (ok[t]) {
+      atomicAdd(Jp + joff[t], jq[t][0]);
+      atomicAdd(Jp + joff[t] + 1, jq[t][1]);
+    }
 }
 
 // dq2[seg_off(k) + l] = 2 * Dtot[k,l] for l <= k, pads = 0
@@ -380,15 +661,53 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
   if (h->timed) cudaEventRecord(h->ev[3], h->stream);
   const int n_i = h->i_hi - h->i_lo;
   if (n_i > 0) {
-    dim3 grid((n + KC - 1) / KC, n_i, (n + 2 * LB - 1) / (2 * LB));
     double* Jp = h->pk_acc;
     double* Kp = h->pk_acc + PQ;
-    if (n_spin == 1)
-      jk_packed_kernel<1><<<grid, LB, 0, h->stream>>>(h->eri, h->pk_btab, h->pk_offset, d_density,
-                                                    h->pk_dq2, Kp, Jp, n, h->i_lo);
-    else
-      jk_packed_kernel<2><<<grid, LB, 0, h->stream>>>(h->eri, h->pk_btab, h->pk_offset, d_density,
-                                                    h->pk_dq2, Kp, Jp, n, h->i_lo);
+    static const int use_tma = [] {  // SCFB_PACKED_TMA=1 selects the bulk-copy ring (v3) kernel
+      const char* v = std::getenv("SCFB_PACKED_TMA");
+      return v ? std::atoi(v) : 0;
+    }();
+    static const int kc_sel = [] {  // tuning knob: SCFB_PACKED_KC=4|8
+      const char* v = std::getenv("SCFB_PACKED_KC");
+      return v ? std::atoi(v) : 0;
+    }();
+    const int kc = kc_sel == 4 || kc_sel == 8 ? kc_sel : (n_spin == 1 ? 4 : 4);
+    if (use_tma && n % 2 == 0) {
+      dim3 tgrid((n + kc - 1) / kc, n_i, (n + LW - 1) / LW);
+      const size_t smem = (size_t)STAGES * kc * LW * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+#define SCFB_PK_TMA(NS, KCV, MINB)                                                               \
+  do {                                                                                           \
+    cudaFuncSetAttribute(jk_packed_tma_kernel<NS, KCV, MINB>,                                    \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
+    jk_packed_tma_kernel<NS, KCV, MINB><<<tgrid, 32 * (CW + 1), smem, h->stream>>>(              \
+        h->eri, h->pk_btab, h->pk_offset, d_density, h->pk_dq2, Kp, Jp, n, h->i_lo);             \
+  } while (0)
+      if (n_spin == 1 && kc == 8) SCFB_PK_TMA(1, 8, 2);
+      else if (n_spin == 1) SCFB_PK_TMA(1, 4, 3);
+      else if (kc == 8) SCFB_PK_TMA(2, 8, 1);
+      else SCFB_PK_TMA(2, 4, 2);
+#undef SCFB_PK_TMA
+      e = cudaGetLastError();
+      if (e != cudaSuccess)
+        return scfb_fail(h, SCFB_ERR_CUDA, "jk_packed_tma_kernel launch: %s", cudaGetErrorString(e));
+      h->launches += 1;
+      if (h->timed) cudaEventRecord(h->ev[1], h->stream);
+      unpack_jk_kernel<<<148 * 2, 256, 0, h->stream>>>(h->pk_acc, h->pk_acc + PQ, h->jk, n, n_spin);
+      e = cudaGetLastError();
+      if (e != cudaSuccess)
+        return scfb_fail(h, SCFB_ERR_CUDA, "unpack_jk_kernel launch: %s", cudaGetErrorString(e));
+      h->launches += 1;
+      return SCFB_OK;
+    }
+    dim3 grid((n + kc - 1) / kc, n_i, (n + 2 * LB - 1) / (2 * LB));
+#define SCFB_PK_LAUNCH(NS, KCV, MINB)                                                         \
+  jk_packed_kernel<NS, KCV, MINB><<<grid, LB, 0, h->stream>>>(h->eri, h->pk_btab, h->pk_offset, \
+                                                             d_density, h->pk_dq2, Kp, Jp, n, h->i_lo)
+    if (n_spin == 1 && kc == 8) SCFB_PK_LAUNCH(1, 8, 2);
+    else if (n_spin == 1) SCFB_PK_LAUNCH(1, 4, 4);
+    else if (kc == 8) SCFB_PK_LAUNCH(2, 8, 2);
+    else SCFB_PK_LAUNCH(2, 4, 3);
+#undef SCFB_PK_LAUNCH
     e = cudaGetLastError();
     if (e != cudaSuccess)
       return scfb_fail(h, SCFB_ERR_CUDA, "jk_packed_kernel launch: %s", cudaGetErrorString(e));
