@@ -1,0 +1,190 @@
+# JKBuilderCUDA.jl — Julia glue for libscf_b200.so (B200-native Fock build).
+#
+# NOTE: Julia is not installed in the environment this repository is built and tested in, so
+# this file has never been executed.  It is deliberately thin: every call below is a 1:1
+# `ccall` of a symbol declared in include/scf_b200.h, and the Python ctypes harness
+# (selfconsistentfield.jl_b200/{capi,builder,scf}.py), which IS tested on B200s, drives exactly
+# the same symbols with the same column-major memory layout.
+#
+# Drop-in boundary (reference files, relative to SelfConsistentField.jl):
+#   src/types/ScfProblem.jl:2-9                  abstract type TwoElectronBuilder, add_2e_term!
+#   src/algorithms/JKBuilderFromTensor.jl:7-51   the builder this one replaces
+#   src/util/load_integral_hdf5.jl:15,51-53      where the default builder is constructed
+#
+# Usage:
+#   include("JKBuilderCUDA.jl"); using .SCFB200
+#   system, integrals = load_integral_hdf5("integrals.hdf5")
+#   integrals = with_cuda_builder(integrals)                  # ERI uploaded once, stays in HBM
+#   problem = assemble_hf_problem(system, integrals)
+#   res = run_scf(problem, compute_guess(problem, system.coords, system.atom_numbers))
+module SCFB200
+
+using SelfConsistentField
+import SelfConsistentField: TwoElectronBuilder, add_2e_term!
+
+export JKBuilderCUDA, with_cuda_builder, jk_split, scf_device_setup!, scf_device_fock!,
+       scf_device_roothaan!, scf_device_diis_push!, scf_device_diis_extrapolate!
+
+const libscf = get(ENV, "SCFB200_LIB", joinpath(@__DIR__, "..", "libscf_b200.so"))
+
+const SCFB_LAYOUT_FULL = Cint(0)
+const SCFB_LAYOUT_PACKED8 = Cint(1)
+const SCFB_ERI_HASH = Cint(0)
+const SCFB_ERI_CHAIN = Cint(1)
+
+last_error(h::Ptr{Cvoid}) = unsafe_string(ccall((:scfb_last_error, libscf), Cstring, (Ptr{Cvoid},), h))
+
+"Turn a non-zero status into a Julia error (the library never throws across the ABI)."
+function check(rc::Cint, h::Ptr{Cvoid}=C_NULL)
+    rc == 0 || error("libscf_b200 ($rc): " * last_error(h))
+    nothing
+end
+
+"""
+J+K builder whose ERI tensor lives in B200 HBM (full fp64 layout or 8-fold packed).
+One builder owns the shard of one GPU: `(rank, n_ranks)` select the nu-slab block.
+"""
+mutable struct JKBuilderCUDA <: TwoElectronBuilder
+    handle::Ptr{Cvoid}
+    n_bas::Int
+    layout::Symbol
+
+    function JKBuilderCUDA(n_bas::Integer; layout::Symbol=:full, device::Integer=0,
+                           rank::Integer=0, n_ranks::Integer=1)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        lay = layout == :full ? SCFB_LAYOUT_FULL : SCFB_LAYOUT_PACKED8
+        check(ccall((:scfb_create, libscf), Cint,
+                    (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint),
+                    h, n_bas, lay, device, rank, n_ranks))
+        obj = new(h[], n_bas, layout)
+        finalizer(obj) do b
+            b.handle == C_NULL || ccall((:scfb_destroy, libscf), Cint, (Ptr{Cvoid},), b.handle)
+            b.handle = C_NULL
+        end
+        obj
+    end
+end
+
+"Equivalent of `JKBuilderFromTensor(eri)`: upload the dense (n,n,n,n) tensor once."
+function JKBuilderCUDA(eri::AbstractArray{Float64,4}; kwargs...)
+    n = size(eri, 1)
+    @assert size(eri) == (n, n, n, n)
+    b = JKBuilderCUDA(n; kwargs...)
+    dense = Array{Float64,4}(eri)       # column-major, exactly the layout the library expects
+    check(ccall((:scfb_eri_upload, libscf), Cint, (Ptr{Cvoid}, Ptr{Float64}), b.handle, dense),
+          b.handle)
+    b
+end
+
+"ERI generated in HBM from a closed-form family (`:hash` or `:chain`), see DESIGN.md."
+function JKBuilderCUDA(n_bas::Integer, family::Symbol, seed::Integer;
+                       aux::Union{Nothing,Vector{Float64}}=nothing, kwargs...)
+    b = JKBuilderCUDA(n_bas; kwargs...)
+    fam = family == :hash ? SCFB_ERI_HASH : SCFB_ERI_CHAIN
+    auxp = aux === nothing ? Ptr{Float64}(C_NULL) : pointer(aux)
+    GC.@preserve aux check(ccall((:scfb_eri_generate, libscf), Cint,
+                                 (Ptr{Cvoid}, Cint, UInt64, Ptr{Float64}),
+                                 b.handle, fam, UInt64(seed), auxp), b.handle)
+    b
+end
+
+"""
+`out[:,:,s] += J[total_density] - K[density[:,:,s]]` — the method the SCF loop reaches through
+`compute_fock_matrix` (src/parts/compute_fock_matrix.jl:31-34).  Same assertions as the
+reference method (src/algorithms/JKBuilderFromTensor.jl:30-32).
+"""
+function add_2e_term!(out::AbstractArray, builder::JKBuilderCUDA,
+                      density::AbstractArray, total_density::AbstractArray)
+    n_bas, _, n_spin = size(density)
+    @assert n_spin == 1 || n_spin == 2
+    @assert size(total_density) == (n_bas, n_bas)
+    @assert size(density) == (n_bas, n_bas, n_spin)
+    @assert n_bas == builder.n_bas
+    d = Array{Float64,3}(density)            # no-op for dense Arrays, copies views
+    t = Array{Float64,2}(total_density)
+    o = out isa Array{Float64,3} ? out : Array{Float64,3}(out)
+    check(ccall((:scfb_fock_jk, libscf), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                builder.handle, n_spin, d, t, o), builder.handle)
+    o === out || (out .= o)
+    out
+end
+
+"J (n,n) and K (n,n,n_spin) separately — for the post-SCF energy split of examples/HartreeFock.jl:88-95."
+function jk_split(builder::JKBuilderCUDA, density::AbstractArray, total_density::AbstractArray)
+    n, _, n_spin = size(density)
+    J = zeros(n, n); K = zeros(n, n, n_spin)
+    check(ccall((:scfb_jk_split, libscf), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                builder.handle, n_spin, Array{Float64,3}(density), Array{Float64,2}(total_density),
+                J, K), builder.handle)
+    J, K
+end
+
+"Replace the default builder of `load_integral_hdf5`'s result by a CUDA one."
+function with_cuda_builder(integrals; kwargs...)
+    merge(integrals, (jk_builder_bb=JKBuilderCUDA(integrals.electron_repulsion_bbbb; kwargs...),))
+end
+
+# ---------------------------------------------------------------------------------------
+# Device-resident SCF step (scfb_scf_*): S, h_core, D, F, error, orbitals and the DIIS history
+# stay in HBM; only scalars, DIIS rows and coefficients cross PCIe.  The caller keeps the
+# control flow of src/run_scf.jl:21-49 and the small solves of cDIIS.jl:33-63 / EDIIS.jl:20-44.
+# ---------------------------------------------------------------------------------------
+function scf_device_setup!(b::JKBuilderCUDA, problem::ScfProblem; n_diis_size::Integer=5)
+    e0 = Float64(sum(v for (k, v) in problem.terms_0e))
+    check(ccall((:scfb_scf_setup, libscf), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cint, Cint, Cint, Cint, Cint),
+                b.handle, Array{Float64,2}(problem.overlap), Array{Float64,2}(problem.h_core), e0,
+                problem.n_elec[1], problem.n_elec[2], problem.n_orb, problem.restricted ? 1 : 0,
+                n_diis_size), b.handle)
+end
+
+function scf_device_set_density!(b::JKBuilderCUDA, density::AbstractArray)
+    check(ccall((:scfb_scf_set_density, libscf), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}),
+                b.handle, size(density, 3), Array{Float64,3}(density)), b.handle)
+end
+
+"compute_fock_matrix on the resident density -> (energies::Dict, error_norm)."
+function scf_device_fock!(b::JKBuilderCUDA)
+    e = zeros(4); nrm = Ref{Cdouble}(0)
+    check(ccall((:scfb_scf_fock, libscf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Cdouble}),
+                b.handle, e, nrm), b.handle)
+    Dict("0e" => e[1], "1e" => e[2], "2e" => e[3], "total" => e[4]), nrm[]
+end
+
+"compute_orbitals + compute_density on the resident Fock iterate (Roothaan.jl:5-6)."
+scf_device_roothaan!(b::JKBuilderCUDA) =
+    check(ccall((:scfb_scf_roothaan, libscf), Cint, (Ptr{Cvoid},), b.handle), b.handle)
+
+"Push the newest (F, e, D) of `spin` (1-based) and return the new cDIIS / EDIIS matrix rows."
+function scf_device_diis_push!(b::JKBuilderCUDA, spin::Integer)
+    m = Ref{Cint}(0); rc = zeros(16); re = zeros(16)
+    check(ccall((:scfb_scf_diis_push, libscf), Cint,
+                (Ptr{Cvoid}, Cint, Ref{Cint}, Ptr{Float64}, Ptr{Float64}),
+                b.handle, spin - 1, m, rc, re), b.handle)
+    rc[1:m[]], re[1:m[]]
+end
+
+"F[:,:,spin] <- sum_i c[i] F_i over the device history, newest first (parts/diis.jl:52-54)."
+scf_device_diis_extrapolate!(b::JKBuilderCUDA, spin::Integer, c::Vector{Float64}) =
+    check(ccall((:scfb_scf_diis_extrapolate, libscf), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}),
+                b.handle, spin - 1, length(c), c), b.handle)
+
+scf_device_diis_purge!(b::JKBuilderCUDA, spin::Integer, count::Integer) =
+    check(ccall((:scfb_scf_diis_purge, libscf), Cint, (Ptr{Cvoid}, Cint, Cint),
+                b.handle, spin - 1, count), b.handle)
+
+scf_device_diis_reset!(b::JKBuilderCUDA) =
+    check(ccall((:scfb_scf_diis_reset, libscf), Cint, (Ptr{Cvoid},), b.handle), b.handle)
+
+"Fetch a resident quantity: 0 fock, 1 fock_new, 2 density, 3 error, 4 orbcoeff, 5 orben (+_PREV 6,7,8)."
+function scf_device_get(b::JKBuilderCUDA, what::Integer, n_spin::Integer)
+    n = b.n_bas
+    out = what in (5, 7) ? zeros(n, n_spin) : zeros(n, n, n_spin)
+    check(ccall((:scfb_scf_get, libscf), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}),
+                b.handle, what, out), b.handle)
+    out
+end
+
+end # module
