@@ -39,12 +39,6 @@ constexpr int LB = 128;  // threads per CTA = 4 independent warps, 256 l values
 __host__ __device__ __forceinline__ uint64_t tri(uint64_t i) { return i * (i + 1) / 2; }
 __host__ __device__ __forceinline__ uint64_t seg_off(uint64_t k) { return tri(k) + (k + 1) / 2; }
 
-__device__ __forceinline__ double2 ldg_stream2(const double* p) {
-  double2 r;
-  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
-  return r;
-}
-
 // Sum V (4 or 8) per-lane values over the 32 lanes of a warp with V+1 (instead of 5V)
 // shuffles: each butterfly stage halves the number of values a lane still carries.
 // On return lanes with (lane % (32/V)) == 0 hold the total of value index lane / (32/V)
@@ -106,36 +100,67 @@ __device__ __forceinline__ double warp_sum(double x) {
   return x;
 }
 
-// One work item of one warp.  D: n x n x NSPIN symmetric; dq2: 2*Dtot in pair space, stored
-// with the SAME padded segment offsets seg_off(k)+l (pads zero).  Kp: n x n x NSPIN
-// accumulators; Jp: accumulators indexed like dq2.
-template <int NSPIN, int KC, bool DIAG>
+// One work item of one warp.  D: (n*n + DPAD) x NSPIN symmetric, padded so that the KC-wide
+// uniform reads D[j, k0..k0+KC) and the pair reads D[j, l0..l0+1] never leave the allocation;
+// dq2: 2*Dtot in pair space, stored with the SAME padded segment offsets seg_off(k)+l (pads
+// zero).  Kp: (n*n + DPAD) x NSPIN accumulators; Jp: accumulators indexed like dq2.
+// MODE 0: interior warp — every lane's pair lies inside every segment of the chunk: no predicates
+// MODE 1: edge warp — per-(t, lane) validity fixed for the item
+// MODE 2: diagonal chunk (k == i inside) — validity also depends on the row j
+//
+// Row sums over the lanes (K'[j,k] and J~[pr(i,j)]) do not use shuffles: every row each lane
+// parks its NV = NSPIN*KC + 1 partial sums in a per-warp shared-memory tile (conflict-free
+// STS), and once RB = 32/NV rows are parked lane r*NV+v adds the 32 partials of (row r,
+// value v) with 16 conflict-free LDS.128 (row stride 34 doubles) in a fixed order and issues
+// the RED.  That is ~13 instructions per row instead of ~56 for shuffle butterflies.
+constexpr int DPAD = 64;
+constexpr int YS = 34;  // padded lane stride of the row-sum tile (doubles)
+constexpr int DEPTH = 4;  // cp.async ring depth (rows)
+// rows parked in the row-sum tile between flushes, and doubles per row of the uniform-D ring
+__host__ __device__ constexpr int packed_rb(int nspin, int kc) {
+  return 32 / (nspin * kc + 1) < 4 ? 32 / (nspin * kc + 1) : 4;
+}
+__host__ __device__ constexpr int packed_dkn(int nspin, int kc) { return (nspin * kc + 2) & ~1; }
+__host__ __device__ constexpr size_t packed_smem_bytes(int nspin, int kc) {
+  return (size_t)(LB / 32) * packed_rb(nspin, kc) * (nspin * kc + 1) * YS * sizeof(double)  // row-sum tiles
+         + (size_t)DEPTH * kc * LB * 16                                                    // ERI ring
+         + (size_t)DEPTH * nspin * LB * 16                                                 // D[j,l] ring
+         + (size_t)DEPTH * (LB / 32) * packed_dkn(nspin, kc) * sizeof(double);             // D[j,k], 2Dtot ring
+}
+
+template <int NSPIN, int KC, int MODE, bool VECD>
 __device__ __forceinline__ void packed_item(const double* __restrict__ eri_i,  // row (i,0)
-                                            const double* __restrict__ D,
+                                            const double* __restrict__ D, size_t dstride,
                                             const double* __restrict__ dq2,
-                                            double* __restrict__ Kp, double* __restrict__ Jp, int n,
-                                            int i, int k0, int l0, int lane, uint32_t rot) {
-  const size_t n2 = (size_t)n * n;
+                                            double* __restrict__ Kp, double* __restrict__ Jp,
+                                            double* __restrict__ ys,  // this warp's 32*YS tile
+                                            double2* __restrict__ ring,     // ERI ring, this thread's slot 0
+                                            double2* __restrict__ ring_dl,  // D[j,l-pair] ring, this thread's slot 0
+                                            double* __restrict__ ring_dk,   // this warp's [DEPTH][DKN] block
+                                            int n, int i, int k0, int l0, int lane, uint32_t rot) {
+  constexpr int NV = NSPIN * KC + 1;
+  constexpr int RB = packed_rb(NSPIN, KC);
+  constexpr int DKN = packed_dkn(NSPIN, KC);
   const int kmax = min(k0 + KC - 1, i);
-  // lanes past the triangle edge (l > kmax, possibly l >= n) only feed zeros to the shuffles
-  const bool l0_in = l0 <= kmax, l1_in = l0 + 1 <= kmax;
+  // lanes past the triangle edge (l > kmax, possibly l >= n) only feed zeros
+  const bool l0_in = MODE == 0 || l0 <= kmax, l1_in = MODE == 0 || l0 + 1 <= kmax;
   const int lc = l0_in ? l0 : 0;
   const uint64_t Ei = seg_off(i);  // elements of the full segments 0..i-1 of every row (i,*)
 
   // per-item constants
   double di_l[NSPIN][2], di_k[NSPIN][KC], dq[KC][2];
-  uint32_t off[KC];
+  uint32_t off[KC];  // element offset of this lane's pair inside a row, per k of the chunk
   bool ok[KC];
 #pragma unroll
   for (int s = 0; s < NSPIN; ++s) {
-    const double* di = D + s * n2 + (size_t)i * n;
+    const double* di = D + s * dstride + (size_t)i * n;
     di_l[s][0] = __ldg(di + lc);
-    di_l[s][1] = l1_in ? __ldg(di + lc + 1) : 0.0;
+    di_l[s][1] = __ldg(di + lc + 1);  // beyond-the-edge values only ever meet zero ERI entries
   }
 #pragma unroll
   for (int t = 0; t < KC; ++t) {
     const int k = k0 + t;
-    ok[t] = k <= i && l0 <= k;
+    ok[t] = MODE == 0 || (k <= i && l0 <= k);
     const int kc = k <= i ? k : i;
     off[t] = (uint32_t)seg_off(kc) + (uint32_t)lc;
     const double2 q2 =
@@ -143,7 +168,7 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_i,  /
     dq[t][0] = q2.x;
     dq[t][1] = q2.y;
 #pragma unroll
-    for (int s = 0; s < NSPIN; ++s) di_k[s][t] = __ldg(D + s * n2 + (size_t)i * n + kc);
+    for (int s = 0; s < NSPIN; ++s) di_k[s][t] = __ldg(D + s * dstride + (size_t)i * n + kc);
   }
 
   double a1[NSPIN][KC], a2[NSPIN][2], jq[KC][2];
@@ -157,109 +182,196 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_i,  /
   for (int s = 0; s < NSPIN; ++s) a2[s][0] = a2[s][1] = 0.0;
 
   const int rows = i + 1;
-  auto load_row = [&](const double* row, int j, double2 (&w)[KC]) {
+  // Everything a row needs travels global -> shared with cp.async (LDGSTS) into a DEPTH-deep
+  // ring, DEPTH-1 rows ahead of its use, so neither the HBM latency of the ERI pairs nor the
+  // L2 latency of the density row (L1 cannot hold D) sits on a row's critical path and no
+  // registers are tied up:  ERI pairs and D[j, l-pair] go to slots only the issuing thread reads
+  // back; the warp-uniform D[j, k0..k0+KC) and 2Dtot[(i,j)] are fetched by the first lanes and
+  // read back as shared-memory broadcasts after a __syncwarp().
+  auto issue_row = [&](int stage, const double* row, const double* dj0, const double* dqp, int j) {
 #pragma unroll
     for (int t = 0; t < KC; ++t) {
-      // the diagonal segment k == i of row (i,j) stops at l = j (padded to even)
-      const bool valid = DIAG ? (ok[t] && (k0 + t < i || l0 <= j)) : ok[t];
-      w[t] = valid ? ldg_stream2(row + off[t]) : make_double2(0.0, 0.0);
+      const bool valid = MODE == 0 ? true : (MODE == 2 ? (ok[t] && (k0 + t < i || l0 <= j)) : ok[t]);
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (stage * KC + t) * LB);
+      const uint32_t nbytes = valid ? 16u : 0u;  // 0 -> the 16 bytes are zero-filled
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(row + off[t]),
+                   "r"(nbytes)
+                   : "memory");
+    }
+#pragma unroll
+    for (int s = 0; s < NSPIN; ++s) {
+      const double* src = dj0 + s * dstride + lc;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring_dl + (stage * NSPIN + s) * LB);
+      if (VECD) {  // n even: (j*n + even) is 16-byte aligned
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8), "l"(src + 1) : "memory");
+      }
+    }
+    if (lane <= NSPIN * KC) {
+      const int s = lane / KC, t = lane - s * KC;
+      const double* src = lane == NSPIN * KC ? dqp : dj0 + s * dstride + k0 + t;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring_dk + stage * DKN + lane);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
     }
   };
 
   // Rows are visited in a rotated order that differs per work item, so that concurrently
   // running warps do not all RED into the same K'[j,:] row at the same time.
-  int j = (int)(rot % (uint32_t)rows);
+  const int j_first = (int)(rot % (uint32_t)rows);
+  // load side (DEPTH-1 rows ahead), warp-uniform
+  int j = j_first;
   const double* row = eri_i + (uint64_t)j * Ei + seg_off(j);
+  const double* dj0 = D + (size_t)j * n;  // D[j, :]   (+ s*dstride per spin)
+  const double* dqp = dq2 + Ei + j;       // 2 Dtot[(i,j)]
+  // consume side
+  int jc = j_first;                       // j of the row being consumed
+  double* kj0 = Kp + (size_t)jc * n;      // K'[j, :]  (+ s*dstride per spin)
+  int parked = 0;                         // rows parked in the tile
+  int j_tile = jc;                        // j of the first parked row
 
-  auto consume = [&](int jj, const double2 (&w)[KC]) {
-    const double dp2 = __ldg(dq2 + Ei + jj);
-    double dj_l[NSPIN][2], dj_k[NSPIN][KC];
+  // lane r*NV + v reduces (row r, value v) of the tile
+  const int red_r = lane / NV, red_v = lane - red_r * NV;
+  auto flush_tile = [&](int n_rows) {
+    __syncwarp();
+    if (red_r < n_rows) {  // (red_r < RB always holds for lanes < RB*NV)
+      const double2* src = reinterpret_cast<const double2*>(ys + lane * YS);
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const double2 v = src[q];
+        acc0 += v.x;
+        acc1 += v.y;
+      }
+      const double tot = acc0 + acc1;
+      int jr = j_tile + red_r;
+      if (jr >= rows) jr -= rows;
+      if (red_v == NV - 1) {
+        atomicAdd(Jp + Ei + jr, tot);  // J~[pr(i,j)]
+      } else {
+        const int sp = red_v / KC, t = red_v - sp * KC;
+        if (MODE == 0 || k0 + t <= i) atomicAdd(Kp + sp * dstride + (size_t)jr * n + k0 + t, tot);  // K'[j,k]
+      }
+    }
+    __syncwarp();
+  };
+
+  auto consume = [&](int stage) {
+    double2 w[KC];
+#pragma unroll
+    for (int t = 0; t < KC; ++t) w[t] = ring[(stage * KC + t) * LB];
+    struct {
+      double dj_l[NSPIN][2], dj_k[NSPIN][KC], dp2;
+    } r;
+    const double* dk = ring_dk + stage * DKN;  // same address in every lane: broadcast reads
+    r.dp2 = dk[NSPIN * KC];
 #pragma unroll
     for (int s = 0; s < NSPIN; ++s) {
-      const double* dj = D + s * n2 + (size_t)jj * n;
-      dj_l[s][0] = __ldg(dj + lc);
-      dj_l[s][1] = l1_in ? __ldg(dj + lc + 1) : 0.0;
+      const double2 v = ring_dl[(stage * NSPIN + s) * LB];
+      r.dj_l[s][0] = v.x;
+      r.dj_l[s][1] = v.y;
 #pragma unroll
-      for (int t = 0; t < KC; ++t) dj_k[s][t] = __ldg(dj + min(k0 + t, i));
+      for (int t = 0; t < KC; t += 2) {
+        const double2 u = *reinterpret_cast<const double2*>(dk + s * KC + t);
+        r.dj_k[s][t] = u.x;
+        r.dj_k[s][t + 1] = u.y;
+      }
     }
     double jp0 = 0.0, jp1 = 0.0;
-    double y[NSPIN][KC], z[NSPIN][2];
+    double z[NSPIN][2];
 #pragma unroll
     for (int s = 0; s < NSPIN; ++s) z[s][0] = z[s][1] = 0.0;
+    double* park = ys + parked * NV * YS + lane;
 #pragma unroll
     for (int t = 0; t < KC; ++t) {
       const double w0 = w[t].x, w1 = w[t].y;
       jp0 = fma(w0, dq[t][0], jp0);
       jp1 = fma(w1, dq[t][1], jp1);
-      jq[t][0] = fma(w0, dp2, jq[t][0]);
-      jq[t][1] = fma(w1, dp2, jq[t][1]);
+      jq[t][0] = fma(w0, r.dp2, jq[t][0]);
+      jq[t][1] = fma(w1, r.dp2, jq[t][1]);
 #pragma unroll
       for (int s = 0; s < NSPIN; ++s) {
-        a1[s][t] = fma(w0, dj_l[s][0], a1[s][t]);
-        a1[s][t] = fma(w1, dj_l[s][1], a1[s][t]);
-        a2[s][0] = fma(w0, dj_k[s][t], a2[s][0]);
-        a2[s][1] = fma(w1, dj_k[s][t], a2[s][1]);
-        y[s][t] = fma(w1, di_l[s][1], w0 * di_l[s][0]);
+        a1[s][t] = fma(w0, r.dj_l[s][0], a1[s][t]);
+        a1[s][t] = fma(w1, r.dj_l[s][1], a1[s][t]);
+        a2[s][0] = fma(w0, r.dj_k[s][t], a2[s][0]);
+        a2[s][1] = fma(w1, r.dj_k[s][t], a2[s][1]);
+        park[(s * KC + t) * YS] = fma(w1, di_l[s][1], w0 * di_l[s][0]);  // -> K'[j,k]
         z[s][0] = fma(w0, di_k[s][t], z[s][0]);
         z[s][1] = fma(w1, di_k[s][t], z[s][1]);
       }
     }
-    // per-row outputs (K' entries are accumulated at whichever of (a,b)/(b,a) coalesces:
-    // K = K' + K'^T does not care)
-#ifndef SCFB_EXP_NO_ROWRED
-    const double jp = warp_sum(jp0 + jp1);
-    if (lane == 0) atomicAdd(Jp + Ei + jj, jp);
-#else
-    a2[0][0] += jp0 + jp1;
-#endif
+    park[(NV - 1) * YS] = jp0 + jp1;  // -> J~[pr(i,j)]
+    // K'[j,l]: lane-private, one RED per lane and row (K' entries are accumulated at
+    // whichever of (a,b)/(b,a) coalesces: K = K' + K'^T does not care)
 #pragma unroll
     for (int s = 0; s < NSPIN; ++s) {
-      double* kj = Kp + s * n2 + (size_t)n * jj;
+      double* kj = kj0 + s * dstride;
 #ifndef SCFB_EXP_NO_Z
-      if (l0_in) atomicAdd(kj + l0, z[s][0]);  // K'[j,l]
+      if (l0_in) atomicAdd(kj + l0, z[s][0]);
       if (l1_in) atomicAdd(kj + l0 + 1, z[s][1]);
 #else
       a2[s][0] += z[s][0] + z[s][1];
-#endif
-#ifndef SCFB_EXP_NO_ROWRED
-      const double r = warp_transpose_reduce<KC>(y[s], lane);
-      const int t = transpose_reduce_index<KC>(lane);
-      if (transpose_reduce_owner<KC>(lane) && k0 + t <= i) atomicAdd(kj + k0 + t, r);  // K'[j,k]
-#else
-#pragma unroll
-      for (int t = 0; t < KC; ++t) a2[s][1] += y[s][t];
       (void)kj;
 #endif
+    }
+#ifdef SCFB_EXP_NO_FLUSH
+    parked = 0;
+#endif
+    if (++parked == RB) {
+      flush_tile(RB);
+      parked = 0;
+      j_tile = jc + 1 == rows ? 0 : jc + 1;
+    }
+    // next consumed row
+    if (jc + 1 == rows) {
+      jc = 0;
+      kj0 = Kp;
+    } else {
+      ++jc;
+      kj0 += n;
     }
   };
   // row (i,j+1) starts E(i) + ceil2(j+1) elements after row (i,j); wraps to row (i,0)
   auto advance = [&]() {
-    const int jn = j + 1 == rows ? 0 : j + 1;
-    row = jn ? row + Ei + ((j + 2) & ~1) : eri_i;
-    j = jn;
+    if (j + 1 == rows) {
+      j = 0;
+      row = eri_i;
+      dj0 = D;
+      dqp = dq2 + Ei;
+    } else {
+      row += Ei + ((j + 2) & ~1);
+      ++j;
+      dj0 += n;
+      ++dqp;
+    }
   };
 
-  // software pipeline, two rows per trip: the loads of the next row are in flight while the
-  // current one is consumed; ping-pong buffers avoid register copies
-  double2 wa[KC], wb[KC];
-  load_row(row, j, wa);
-  int step = 0;
-  for (; step + 2 <= rows; step += 2) {
-    const int ja = j;
-    advance();
-    load_row(row, j, wb);
-    consume(ja, wa);
-    const int jb = j;
-    advance();
-    if (step + 2 < rows) load_row(row, j, wa);
-    consume(jb, wb);
+  // prologue: DEPTH-1 rows in flight (empty groups keep the group count uniform)
+#pragma unroll
+  for (int d = 0; d < DEPTH - 1; ++d) {
+    if (d < rows) {
+      issue_row(d, row, dj0, dqp, j);
+      advance();
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  if (step < rows) consume(j, wa);
+  for (int step = 0; step < rows; ++step) {
+    if (step + DEPTH - 1 < rows) {
+      issue_row((step + DEPTH - 1) % DEPTH, row, dj0, dqp, j);
+      advance();
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+    __syncwarp();  // the uniform values were fetched by other lanes
+    consume(step % DEPTH);
+  }
+  if (parked) flush_tile(parked);
 
   // per-item outputs
 #pragma unroll
   for (int s = 0; s < NSPIN; ++s) {
-    double* ki = Kp + s * n2 + (size_t)n * i;
+    double* ki = Kp + s * dstride + (size_t)n * i;
     if (l0_in) atomicAdd(ki + l0, a2[s][0]);  // K'[i,l]
     if (l1_in) atomicAdd(ki + l0 + 1, a2[s][1]);
     const double r = warp_transpose_reduce<KC>(a1[s], lane);
@@ -275,27 +387,41 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_i,  /
 }
 
 // grid = (n_kchunks, n_i_owned, n_lblocks), block = LB threads = 4 independent warps.
-template <int NSPIN, int KC, int MINB>
+template <int NSPIN, int KC, int MINB, bool VECD>
 __global__ void __launch_bounds__(LB, MINB)
 jk_packed_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Btab,
-                 uint64_t shard_offset, const double* __restrict__ D,
+                 uint64_t shard_offset, const double* __restrict__ D, size_t dstride,
                  const double* __restrict__ dq2, double* __restrict__ Kp, double* __restrict__ Jp,
                  int n, int i_lo) {
+  extern __shared__ __align__(16) unsigned char pk_smem[];
+  constexpr int TILE = packed_rb(NSPIN, KC) * (NSPIN * KC + 1) * YS;  // doubles per warp
+  constexpr int DKN = packed_dkn(NSPIN, KC);
+  double* ys_all = reinterpret_cast<double*>(pk_smem);                                // [warps][TILE]
+  double2* ring_all = reinterpret_cast<double2*>(ys_all + (LB / 32) * TILE);          // [DEPTH][KC][LB]
+  double2* ring_dl_all = ring_all + DEPTH * KC * LB;                                  // [DEPTH][NSPIN][LB]
+  double* ring_dk_all = reinterpret_cast<double*>(ring_dl_all + DEPTH * NSPIN * LB);  // [warps][DEPTH][DKN]
   const int i = i_lo + blockIdx.y;
   const int k0 = blockIdx.x * KC;
   if (k0 > i) return;
   const int m = blockIdx.z * LB + threadIdx.x;  // l-pair index
   const int lane = threadIdx.x & 31;
   const int kmax = min(k0 + KC - 1, i);
-  if (2 * (m & ~31) > kmax) return;  // whole warp beyond the triangle
+  const int wl = 2 * (m & ~31);  // first l of this warp
+  if (wl > kmax) return;         // whole warp beyond the triangle
   const int l0 = 2 * m;
   const double* eri_i = eri + (Btab[i] - shard_offset);
+  double* ys = ys_all + (threadIdx.x >> 5) * TILE;
+  double2* ring = ring_all + threadIdx.x;
+  double2* ring_dl = ring_dl_all + threadIdx.x;
+  double* ring_dk = ring_dk_all + (threadIdx.x >> 5) * DEPTH * DKN;
   const uint32_t rot =
       blockIdx.x * 40503u + blockIdx.z * 9973u + blockIdx.y * 17u + (threadIdx.x >> 5) * 7u;
-  if (kmax < i)
-    packed_item<NSPIN, KC, false>(eri_i, D, dq2, Kp, Jp, n, i, k0, l0, lane, rot);
+  if (kmax == i)
+    packed_item<NSPIN, KC, 2, VECD>(eri_i, D, dstride, dq2, Kp, Jp, ys, ring, ring_dl, ring_dk, n, i, k0, l0, lane, rot);
+  else if (wl + 63 <= k0)
+    packed_item<NSPIN, KC, 0, VECD>(eri_i, D, dstride, dq2, Kp, Jp, ys, ring, ring_dl, ring_dk, n, i, k0, l0, lane, rot);
   else
-    packed_item<NSPIN, KC, true>(eri_i, D, dq2, Kp, Jp, n, i, k0, l0, lane, rot);
+    packed_item<NSPIN, KC, 1, VECD>(eri_i, D, dstride, dq2, Kp, Jp, ys, ring, ring_dl, ring_dk, n, i, k0, l0, lane, rot);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -503,7 +629,7 @@ jk_packed_tma_kernel(const double* __restrict__ eri, const uint64_t* __restrict_
     if (lane == 0) atomicAdd(Jp + Ei + j, jp);
 #pragma unroll
     for (int sp = 0; sp < NSPIN; ++sp) {
-      double* kj = Kp + sp * n2 + (size_t)n * j;
+      double* kj = Kp + sp * (n2 + DPAD) + (size_t)n * j;
       if (l0_in) atomicAdd(kj + l0, z[sp][0]);  // K'[j,l]
       if (l1_in) atomicAdd(kj + l0 + 1, z[sp][1]);
       const double r = warp_transpose_reduce<KC>(y[sp], lane);
@@ -515,7 +641,7 @@ jk_packed_tma_kernel(const double* __restrict__ eri, const uint64_t* __restrict_
 
 #pragma unroll
   for (int sp = 0; sp < NSPIN; ++sp) {
-    double* ki = Kp + sp * n2 + (size_t)n * i;
+    double* ki = Kp + sp * (n2 + DPAD) + (size_t)n * i;
     if (l0_in) atomicAdd(ki + l0, a2[sp][0]);  // K'[i,l]
     if (l1_in) atomicAdd(ki + l0 + 1, a2[sp][1]);
     const double r = warp_transpose_reduce<KC>(a1[sp], lane);
@@ -530,13 +656,22 @@ jk_packed_tma_kernel(const double* __restrict__ eri, const uint64_t* __restrict_
     }
 }
 
-// dq2[seg_off(k) + l] = 2 * Dtot[k,l] for l <= k, pads = 0
-__global__ void pack_density_kernel(const double* __restrict__ dtot, double* __restrict__ dq2, int n) {
+// dq2[seg_off(k) + l] = 2 * Dtot[k,l] for l <= k, pads = 0;  dpad = D with DPAD zeros appended
+// to every spin block (lets the kernel read D[j, k0..k0+KC) without clamping)
+__global__ void pack_density_kernel(const double* __restrict__ dtot, const double* __restrict__ dens,
+                                    double* __restrict__ dq2, double* __restrict__ dpad, int n,
+                                    int n_spin) {
   for (int k = blockIdx.x; k < n; k += gridDim.x) {
     const uint64_t base = seg_off(k);
     const int len = (k + 2) & ~1;
     for (int l = threadIdx.x; l < len; l += blockDim.x)
       dq2[base + l] = l <= k ? 2.0 * dtot[k + (size_t)n * l] : 0.0;
+    for (int s = 0; s < n_spin; ++s) {
+      const size_t src = (size_t)s * n * n + (size_t)k * n, dst = (size_t)s * ((size_t)n * n + DPAD) + (size_t)k * n;
+      for (int l = threadIdx.x; l < n; l += blockDim.x) dpad[dst + l] = dens[src + l];
+      if (k == n - 1)
+        for (int l = threadIdx.x; l < DPAD; l += blockDim.x) dpad[dst + n + l] = 0.0;
+    }
   }
 }
 
@@ -550,7 +685,8 @@ __global__ void unpack_jk_kernel(const double* __restrict__ Jp, const double* __
     const size_t hi = a > b ? a : b, lo = a > b ? b : a;
     // a diagonal pair (a,a) is the target of both the (ab|..) and (ba|..) permutations
     jk[e] = (a == b ? 2.0 : 1.0) * Jp[seg_off(hi) + lo];
-    for (int s = 0; s < n_spin; ++s) jk[(1 + s) * n2 + e] = Kp[s * n2 + e] + Kp[s * n2 + b + n * a];
+    for (int s = 0; s < n_spin; ++s)
+      jk[(1 + s) * n2 + e] = Kp[s * (n2 + DPAD) + e] + Kp[s * (n2 + DPAD) + b + n * a];
   }
 }
 
@@ -654,9 +790,10 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
   const uint64_t PQ = seg_off(n);
   cudaError_t e;
   // zero the accumulators: [J~ (PQ) | K' (2 n^2)]
-  e = cudaMemsetAsync(h->pk_acc, 0, (PQ + 2 * n2) * sizeof(double), h->stream);
+  e = cudaMemsetAsync(h->pk_acc, 0, (PQ + 2 * (n2 + DPAD)) * sizeof(double), h->stream);
   if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
-  pack_density_kernel<<<n < 296 ? n : 296, 128, 0, h->stream>>>(d_total, h->pk_dq2, n);
+  pack_density_kernel<<<n < 296 ? n : 296, 128, 0, h->stream>>>(d_total, d_density, h->pk_dq2, h->pk_dpad, n, n_spin);
+  const size_t dstride = n2 + DPAD;
   h->launches += 1;
   if (h->timed) cudaEventRecord(h->ev[3], h->stream);
   const int n_i = h->i_hi - h->i_lo;
@@ -667,11 +804,15 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
       const char* v = std::getenv("SCFB_PACKED_TMA");
       return v ? std::atoi(v) : 0;
     }();
+    static const int minb_sel = [] {  // tuning knob: SCFB_PACKED_MINB=3|4 (CTAs per SM, KC=4 RHF)
+      const char* v = std::getenv("SCFB_PACKED_MINB");
+      return v ? std::atoi(v) : 4;
+    }();
     static const int kc_sel = [] {  // tuning knob: SCFB_PACKED_KC=4|8
       const char* v = std::getenv("SCFB_PACKED_KC");
       return v ? std::atoi(v) : 0;
     }();
-    const int kc = kc_sel == 4 || kc_sel == 8 ? kc_sel : (n_spin == 1 ? 4 : 4);
+    const int kc = kc_sel == 4 || kc_sel == 8 ? kc_sel : 8;
     if (use_tma && n % 2 == 0) {
       dim3 tgrid((n + kc - 1) / kc, n_i, (n + LW - 1) / LW);
       const size_t smem = (size_t)STAGES * kc * LW * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
@@ -700,10 +841,24 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
       return SCFB_OK;
     }
     dim3 grid((n + kc - 1) / kc, n_i, (n + 2 * LB - 1) / (2 * LB));
-#define SCFB_PK_LAUNCH(NS, KCV, MINB)                                                         \
-  jk_packed_kernel<NS, KCV, MINB><<<grid, LB, 0, h->stream>>>(h->eri, h->pk_btab, h->pk_offset, \
-                                                             d_density, h->pk_dq2, Kp, Jp, n, h->i_lo)
+#define SCFB_PK_LAUNCH(NS, KCV, MINB)                                                          \
+  do {                                                                                          \
+    const size_t sm_ = packed_smem_bytes(NS, KCV);                                              \
+    if (n % 2 == 0) {                                                                           \
+      cudaFuncSetAttribute(jk_packed_kernel<NS, KCV, MINB, true>,                               \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_);              \
+      jk_packed_kernel<NS, KCV, MINB, true><<<grid, LB, sm_, h->stream>>>(                      \
+          h->eri, h->pk_btab, h->pk_offset, h->pk_dpad, dstride, h->pk_dq2, Kp, Jp, n, h->i_lo); \
+    } else {                                                                                    \
+      cudaFuncSetAttribute(jk_packed_kernel<NS, KCV, MINB, false>,                              \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_);              \
+      jk_packed_kernel<NS, KCV, MINB, false><<<grid, LB, sm_, h->stream>>>(                     \
+          h->eri, h->pk_btab, h->pk_offset, h->pk_dpad, dstride, h->pk_dq2, Kp, Jp, n, h->i_lo); \
+    }                                                                                           \
+  } while (0)
     if (n_spin == 1 && kc == 8) SCFB_PK_LAUNCH(1, 8, 2);
+    else if (n_spin == 1 && minb_sel == 3) SCFB_PK_LAUNCH(1, 4, 3);
+    else if (n_spin == 1 && minb_sel == 2) SCFB_PK_LAUNCH(1, 4, 2);
     else if (n_spin == 1) SCFB_PK_LAUNCH(1, 4, 4);
     else if (kc == 8) SCFB_PK_LAUNCH(2, 8, 2);
     else SCFB_PK_LAUNCH(2, 4, 3);

@@ -122,8 +122,9 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
   if (h->kpart_elems) CREATE_CUDA(cudaMalloc(&h->kpart, h->kpart_elems * sizeof(double)));
   if (layout == SCFB_LAYOUT_PACKED8) {
     const uint64_t PQ = scfb_packed_dq_elems(n_bas);
-    CREATE_CUDA(cudaMalloc(&h->pk_acc, (PQ + 2 * n2) * sizeof(double)));
+    CREATE_CUDA(cudaMalloc(&h->pk_acc, (PQ + 2 * (n2 + 64)) * sizeof(double)));
     CREATE_CUDA(cudaMalloc(&h->pk_dq2, PQ * sizeof(double)));
+    CREATE_CUDA(cudaMalloc(&h->pk_dpad, 2 * (n2 + 64) * sizeof(double)));
     if (int rc_ = scfb_packed_upload_table(h)) {
       scfb_destroy(h);
       return rc_;
@@ -149,6 +150,7 @@ int scfb_destroy(scfb_handle_t h) {
   cudaFree(h->kpart);
   cudaFree(h->pk_acc);
   cudaFree(h->pk_dq2);
+  cudaFree(h->pk_dpad);
   cudaFree(h->pk_btab);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   for (auto& ev : h->ev)

@@ -23,6 +23,7 @@ struct scfb_handle_s {
   uint64_t pk_offset = 0;       // packed elements stored before this shard
   double* pk_acc = nullptr;     // [J~ (P) | K' (2 n^2)] fp64 RED accumulators
   double* pk_dq2 = nullptr;     // 2*Dtot in (padded) pair space
+  double* pk_dpad = nullptr;    // padded copy of D (2 x (n^2 + 64))
   uint64_t* pk_btab = nullptr;  // B[i]: offset of row (i,0), n+1 entries
 
   double* eri = nullptr;  // device shard
