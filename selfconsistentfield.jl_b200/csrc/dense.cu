@@ -183,6 +183,22 @@ int pulay_block(scfb_handle_s* h, scfb_scf_state* st, const double* F, const dou
   return gemm(h, st, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, -1.0, F, n, st->T2, n, 1.0, E, n);
 }
 
+int ensure_dense_handles(scfb_handle_s* h) {
+  if (!h->blas) {
+    cublasHandle_t b = nullptr;
+    SCFB_BLAS(h, cublasCreate(&b));
+    h->blas = b;
+  }
+  if (!h->solver) {
+    cusolverDnHandle_t sv = nullptr;
+    SCFB_SOLVER(h, cusolverDnCreate(&sv));
+    h->solver = sv;
+  }
+  cublasSetStream(static_cast<cublasHandle_t>(h->blas), h->stream);
+  cusolverDnSetStream(static_cast<cusolverDnHandle_t>(h->solver), h->stream);
+  return SCFB_OK;
+}
+
 int require_state(scfb_handle_s* h) {
   if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
   if (!h->scf) return scfb_fail(h, SCFB_ERR_STATE, "scfb_scf_setup has not been called");
@@ -204,10 +220,15 @@ void scfb_scf_free(scfb_handle_s* h) {
     cudaFree(p);
   cudaFree(st->dev_info);
   if (st->h_scal) cudaFreeHost(st->h_scal);
-  if (st->blas) cublasDestroy(st->blas);
-  if (st->solver) cusolverDnDestroy(st->solver);
   delete st;
   h->scf = nullptr;
+}
+
+// cuBLAS / cuSOLVER handle creation costs tens of milliseconds: done once per scfb handle
+void scfb_dense_handles_destroy(scfb_handle_s* h) {
+  if (h->blas) cublasDestroy(static_cast<cublasHandle_t>(h->blas));
+  if (h->solver) cusolverDnDestroy(static_cast<cusolverDnHandle_t>(h->solver));
+  h->blas = h->solver = nullptr;
 }
 
 extern "C" {
@@ -239,8 +260,9 @@ int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core,
   st->e0 = e_0e;
   st->cap = n_diis_size;
   const size_t n2 = (size_t)n * n;
-  SCFB_BLAS(h, cublasCreate(&st->blas));
-  SCFB_SOLVER(h, cusolverDnCreate(&st->solver));
+  if (int rc = ensure_dense_handles(h)) return rc;
+  st->blas = static_cast<cublasHandle_t>(h->blas);
+  st->solver = static_cast<cusolverDnHandle_t>(h->solver);
   cublasSetStream(st->blas, h->stream);
   cusolverDnSetStream(st->solver, h->stream);
   auto alloc = [&](double** p, size_t count) { return cudaMalloc(p, count * sizeof(double)); };
@@ -547,12 +569,12 @@ int scfb_pulay_error(scfb_handle_t h, int n_spin, const double* fock, const doub
   double* F = buf + 3 * n2;
   double* D = F + n_spin * n2;
   double* E = D + n_spin * n2;
-  int rc = SCFB_OK;
-  if (cublasCreate(&tmp.blas) != CUBLAS_STATUS_SUCCESS) {
+  int rc = ensure_dense_handles(h);
+  if (rc) {
     cudaFree(buf);
-    return scfb_fail(h, SCFB_ERR_CUSOLVER, "cublasCreate failed");
+    return rc;
   }
-  cublasSetStream(tmp.blas, h->stream);
+  tmp.blas = static_cast<cublasHandle_t>(h->blas);
   cudaMemcpyAsync(tmp.S, overlap, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
   cudaMemcpyAsync(F, fock, n_spin * n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
   cudaMemcpyAsync(D, density, n_spin * n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
@@ -560,7 +582,6 @@ int scfb_pulay_error(scfb_handle_t h, int n_spin, const double* fock, const doub
     rc = pulay_block(h, &tmp, F + s * n2, D + s * n2, E + s * n2);
   cudaMemcpyAsync(error_out, E, n_spin * n2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
   cudaError_t e = cudaStreamSynchronize(h->stream);
-  cublasDestroy(tmp.blas);
   cudaFree(buf);
   if (rc) return rc;
   if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "pulay_error: %s", cudaGetErrorString(e));
@@ -577,10 +598,8 @@ int scfb_sygvd(scfb_handle_t h, int n_spin, int n_orb, const double* fock, const
                       n_orb >= 1 && n_orb <= n, "bad arguments");
   SCFB_CUDA(h, cudaSetDevice(h->device));
   const size_t n2 = (size_t)n * n;
-  cusolverDnHandle_t solver = nullptr;
-  if (cusolverDnCreate(&solver) != CUSOLVER_STATUS_SUCCESS)
-    return scfb_fail(h, SCFB_ERR_CUSOLVER, "cusolverDnCreate failed");
-  cusolverDnSetStream(solver, h->stream);
+  if (int rc0 = ensure_dense_handles(h)) return rc0;
+  cusolverDnHandle_t solver = static_cast<cusolverDnHandle_t>(h->solver);
   double* buf = nullptr;
   int* info_d = nullptr;
   int lwork = 0, rc = SCFB_OK, info = 0;
@@ -609,7 +628,6 @@ int scfb_sygvd(scfb_handle_t h, int n_spin, int n_orb, const double* fock, const
   cudaFree(work);
   cudaFree(info_d);
   cudaFree(buf);
-  cusolverDnDestroy(solver);
   if (rc) return rc;
   if (e != cudaSuccess) return scfb_fail(h, e == cudaErrorMemoryAllocation ? SCFB_ERR_OOM : SCFB_ERR_CUDA,
                                          "sygvd: %s", cudaGetErrorString(e));

@@ -135,13 +135,14 @@ __device__ __forceinline__ void stream_rows(const double* __restrict__ xbase,
 }
 
 // grid = (n_chunks, n_slabs); block = roundup32(R*G) threads; dynamic smem = kred.
-template <int VEC, int NSPIN>
-__global__ void __launch_bounds__(MAX_THREADS, 2)
+// MAXT = 256 (2 CTAs/SM) covers rows of up to 512 doubles; MAXT = 512 (1 CTA/SM) rows up to 1024.
+template <int VEC, int NSPIN, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 256 ? 2 : 1)
 jk_full_stream_kernel(const double* __restrict__ eri, const double* __restrict__ dtot,
                       const double* __restrict__ dens, double* __restrict__ jk,
                       double* __restrict__ kpart, int n, int nu_lo, int R, int G) {
   extern __shared__ double kred[];  // [G][NSPIN][n] when G > 1
-  __shared__ double jred[MAX_THREADS / 32][TC];
+  __shared__ double jred[MAXT / 32][TC];
 
   const int tid = threadIdx.x;
   const int g = tid / R;
@@ -236,19 +237,19 @@ __global__ void accumulate_kernel(const double* __restrict__ jk, double* __restr
   }
 }
 
-template <int VEC, int NSPIN>
+template <int VEC, int NSPIN, int MAXT>
 cudaError_t launch_stream(scfb_handle_s* h, const double* d_density, const double* d_total) {
   const int n = h->n;
   const int n_slabs = h->nu_hi - h->nu_lo;
   const int n_chunks = (n + TC - 1) / TC;
   const int R = (n + VEC - 1) / VEC;
-  int G = MAX_THREADS / R;
+  int G = MAXT / R;
   if (G < 1) G = 1;
   if (G > n) G = n;
   const int threads = ((R * G + 31) / 32) * 32;
   const size_t smem = G > 1 ? (size_t)G * NSPIN * n * sizeof(double) : 0;
   dim3 grid(n_chunks, n_slabs);
-  jk_full_stream_kernel<VEC, NSPIN><<<grid, threads, smem, h->stream>>>(
+  jk_full_stream_kernel<VEC, NSPIN, MAXT><<<grid, threads, smem, h->stream>>>(
       h->eri, d_total, d_density, h->jk, h->kpart, n, h->nu_lo, R, G);
   return cudaGetLastError();
 }
@@ -274,12 +275,19 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
   // rows longer than 2*MAX_THREADS are rejected at create time.
   cudaError_t e;
   if (h->timed) cudaEventRecord(h->ev[3], h->stream);
-  if (even)
-    e = n_spin == 1 ? launch_stream<2, 1>(h, d_density, d_total)
-                    : launch_stream<2, 2>(h, d_density, d_total);
+  const bool wide = (even ? n / 2 : n) > MAX_THREADS;  // rows longer than one 256-thread pass
+  if (even && !wide)
+    e = n_spin == 1 ? launch_stream<2, 1, 256>(h, d_density, d_total)
+                    : launch_stream<2, 2, 256>(h, d_density, d_total);
+  else if (even)
+    e = n_spin == 1 ? launch_stream<2, 1, 512>(h, d_density, d_total)
+                    : launch_stream<2, 2, 512>(h, d_density, d_total);
+  else if (!wide)
+    e = n_spin == 1 ? launch_stream<1, 1, 256>(h, d_density, d_total)
+                    : launch_stream<1, 2, 256>(h, d_density, d_total);
   else
-    e = n_spin == 1 ? launch_stream<1, 1>(h, d_density, d_total)
-                    : launch_stream<1, 2>(h, d_density, d_total);
+    e = n_spin == 1 ? launch_stream<1, 1, 512>(h, d_density, d_total)
+                    : launch_stream<1, 2, 512>(h, d_density, d_total);
   if (e != cudaSuccess)
     return scfb_fail(h, SCFB_ERR_CUDA, "jk_full_stream_kernel launch: %s", cudaGetErrorString(e));
   if (h->timed) cudaEventRecord(h->ev[1], h->stream);

@@ -66,8 +66,8 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
   SCFB_REQUIRE(nullptr, n_ranks >= 1 && rank >= 0 && rank < n_ranks, "bad rank %d of %d", rank,
                n_ranks);
   if (layout == SCFB_LAYOUT_FULL)
-    SCFB_REQUIRE(nullptr, (n_bas % 2 == 0 && n_bas <= 512) || (n_bas % 2 == 1 && n_bas <= 255),
-                 "n_bas=%d unsupported by the full layout: even n <= 512 or odd n <= 255", n_bas);
+    SCFB_REQUIRE(nullptr, (n_bas % 2 == 0 && n_bas <= 1024) || (n_bas % 2 == 1 && n_bas <= 511),
+                 "n_bas=%d unsupported by the full layout: even n <= 1024 or odd n <= 511", n_bas);
   else
     SCFB_REQUIRE(nullptr, n_bas <= 2048, "n_bas=%d unsupported by the packed8 layout: n <= 2048", n_bas);
   int n_dev = 0;
@@ -143,6 +143,7 @@ int scfb_destroy(scfb_handle_t h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   scfb_comm_destroy(h);
   scfb_scf_free(h);
+  scfb_dense_handles_destroy(h);
   cudaFree(h->eri);
   cudaFree(h->d_density);
   if (h->jk_sum != h->jk) cudaFree(h->jk_sum);

@@ -47,6 +47,8 @@ struct scfb_handle_s {
   uint64_t launches = 0;
 
   scfb_scf_state* scf = nullptr;  // device-resident SCF step (scfb_scf_setup)
+  void* blas = nullptr;           // cublasHandle_t, created on first use
+  void* solver = nullptr;         // cusolverDnHandle_t, created on first use
 
   void* nccl_comm = nullptr;  // ncclComm_t when n_ranks > 1 and initialised
 
@@ -108,3 +110,4 @@ int scfb_comm_allreduce_jk(scfb_handle_s* h, int n_spin);
 int scfb_comm_destroy(scfb_handle_s* h);
 // dense.cu
 void scfb_scf_free(scfb_handle_s* h);
+void scfb_dense_handles_destroy(scfb_handle_s* h);

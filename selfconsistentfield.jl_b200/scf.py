@@ -406,9 +406,15 @@ class EDIIS(_Diis):
             c = x ** 2 / np.sum(x ** 2)
             return e @ c - 0.5 * c @ b @ c
 
+        def grad(x):   # exact derivative (the reference uses forward-mode AD, EDIIS.jl:33)
+            s2 = np.sum(x ** 2)
+            c = x ** 2 / s2
+            g_c = e - b @ c                                   # d f / d c   (b symmetric)
+            return 2 * x / s2 * (g_c - c @ g_c)               # chain rule through c = x^2 / sum x^2
+
         guess = np.ones(m) / m
         guess[0] = 1
-        res = scipy.optimize.minimize(f, guess, method="BFGS", options={"xrtol": 1e-4})
+        res = scipy.optimize.minimize(f, guess, jac=grad, method="BFGS", options={"xrtol": 1e-4})
         c = res.x ** 2 / np.sum(res.x ** 2)
         if res.nit == 0:
             c = np.zeros(m)

@@ -212,3 +212,29 @@ def test_error_behaviour():
     b.close()
     with pytest.raises(scf_b200.ScfbError):
         scf_b200.JKBuilderCUDA(6, device=99)
+
+
+# ---- rows wider than one 256-thread pass (even n > 512, odd n > 255): 512-thread variant -----
+@pytest.mark.parametrize("n,n_ranks", [(520, 130), (301, 43)])
+def test_wide_rows_known_answers_on_a_shard(n, n_ranks):
+    """The full tensor would be 0.6 TB / 66 GB; rank 0 of `n_ranks` owns only a few nu-slabs,
+    whose J/K columns have exact closed-form answers for unit densities (hash family)."""
+    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, rank=0, n_ranks=n_ranks)
+    lo, hi = b.shard_range
+    assert lo == 0 and 0 < hi <= 8
+    idx = np.arange(n)
+    unit = lambda a, c: (lambda m: (m.__setitem__((a, c), 1.0), m)[1])(np.zeros((n, n)))
+    a0, b0, a1, b1 = 5, n - 3, n - 1, 7
+    j, k = b.jk(unit(a1, b1)[:, :, None], unit(a0, b0))
+    own = np.arange(lo, hi)
+    assert np.array_equal(j[:, lo:hi], synth.hash_eri_elements(a0, b0, idx[:, None], own[None, :]))
+    assert np.array_equal(k[:, lo:hi, 0], synth.hash_eri_elements(idx[:, None], b1, a1, own[None, :]))
+    assert not j[:, hi:].any() and not k[:, hi:, :].any()
+    # a dense density: linearity against the two halves
+    d = synth.hash_symmetric_matrix(n, 5)
+    d1 = np.triu(d)
+    j_full, k_full = b.jk(d[:, :, None], d)
+    j_a, k_a = b.jk(d1[:, :, None], d1)
+    j_b, k_b = b.jk((d - d1)[:, :, None], d - d1)
+    assert rel_err(j_a + j_b, j_full) < RTOL and rel_err(k_a + k_b, k_full) < RTOL
+    b.close()

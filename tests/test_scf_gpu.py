@@ -212,3 +212,27 @@ def test_termwise_energies_match_oracle(golden_dir):
     ej, ek = o.termwise_jk_energies(integrals["electron_repulsion_bbbb"], res["density"])
     assert abs(en["coulomb"] - ej) < 1e-11 and abs(en["exchange"] - ek) < 1e-11
     assert abs(en["coulomb"] + en["exchange"] - en["2e"]) < 1e-6      # stale iterate vs its density
+
+
+def test_config2_n128_chain_rhf_complete_scf():
+    """BASELINE.json config 2: synthetic RHF n_bf=128, full fp64 ERI (2.1 GB generated in HBM),
+    complete SCF loop with EDIIS -> cDIIS on the device; energy vs the CPU oracle to 1e-10 Eh."""
+    n = 128
+    model = scf_b200.synthetic.ChainModel(n)
+    builder = scf_b200.JKBuilderCUDA.synthetic(n, "chain", 0, aux=model.aux)
+    assert builder.eri_bytes == 8 * n ** 4
+    problem = scf_b200.ScfProblem(model.overlap, model.n_elec(), n, True,
+                                  {"nuclear_repulsion": model.nuclear_repulsion},
+                                  {"kinetic": model.kinetic, "nuclear_attraction": model.nuclear_attraction},
+                                  {"coulomb+exchange": builder})
+    kw = dict(max_error_norm=1e-9, max_energy_total_change=1e-11, max_iter=200)
+    res = scf_b200.run_scf(problem, scf_b200.compute_guess(problem), verbose=False, **kw)
+    x, s, t, v, enn = synth.chain_matrices(n)
+    op = o.ScfProblem(s, (n // 2, n // 2), n, True, {"nuclear_repulsion": enn},
+                      {"kinetic": t, "nuclear_attraction": v},
+                      {"coulomb+exchange": o.JKBuilderFromTensor(synth.chain_eri(n))})
+    ref = o.run_scf(op, o.compute_guess_hcore(op), **kw)
+    assert res["converged"] and ref["converged"] and res["mode"] == "device"
+    assert abs(res["energies_newest"]["total"] - ref["energies_newest"]["total"]) < 1e-10
+    assert abs(res["energies_newest"]["total"] - (-85.2054609659)) < 1e-9     # SURVEY Appendix F
+    builder.close()
