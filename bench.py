@@ -262,7 +262,18 @@ def run_ours(a, rank, local_rank, world):
 
         # end to end through the public host-pointer API (pinned staging inside the library)
         e2e_steps = a.e2e_steps or a.steps
-        out_h = np.zeros((n, n, n_spin), order="F")
+
+        def pinned_like(arr):    # page-locked host copy with the same column-major layout
+            t = torch.empty(arr.T.shape, dtype=torch.float64, pin_memory=True)
+            view = t.numpy().T
+            view[...] = arr
+            return t, view
+
+        _keep_d, dens_p = pinned_like(dens_h)
+        _keep_t, total_p = pinned_like(total_h)
+        _keep_o, out_h = pinned_like(np.zeros((n, n, n_spin), order="F"))
+        assert out_h.flags.f_contiguous and dens_p.flags.f_contiguous
+        dens_h, total_h = dens_p, total_p
         for _ in range(min(3, a.warmup)):
             builder.add_2e_term(out_h, dens_h, total_h)
         barrier()

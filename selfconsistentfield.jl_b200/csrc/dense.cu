@@ -12,6 +12,7 @@
 #include <cublas_v2.h>
 #include <cusolverDn.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "scfb_internal.h"
@@ -34,6 +35,9 @@ struct scfb_scf_state {
   double *T1 = nullptr, *T2 = nullptr, *Bw = nullptr;      // n^2 scratch
   double *work = nullptr;
   int lwork = 0;
+  syevjInfo_t jacobi = nullptr;  // SCFB_EIG=jacobi: cusolverDnDsygvj instead of Dsygvd
+  double* work_j = nullptr;
+  int lwork_j = 0;
   int* dev_info = nullptr;
   double* scal = nullptr;    // device scalars
   double* h_scal = nullptr;  // pinned mirror
@@ -219,6 +223,8 @@ void scfb_scf_free(scfb_handle_s* h) {
                     st->Cprev, st->epsprev, st->Dprev})
     cudaFree(p);
   cudaFree(st->dev_info);
+  cudaFree(st->work_j);
+  if (st->jacobi) cusolverDnDestroySyevjInfo(st->jacobi);
   if (st->h_scal) cudaFreeHost(st->h_scal);
   delete st;
   h->scf = nullptr;
@@ -293,6 +299,16 @@ int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core,
                                              CUBLAS_FILL_MODE_LOWER, n, st->T1, n, st->Bw, n, st->eps,
                                              &st->lwork));
   SCFB_CUDA(h, alloc(&st->work, st->lwork > 0 ? st->lwork : 1));
+  if (const char* eig = std::getenv("SCFB_EIG"); eig && std::strcmp(eig, "jacobi") == 0) {
+    SCFB_SOLVER(h, cusolverDnCreateSyevjInfo(&st->jacobi));
+    SCFB_SOLVER(h, cusolverDnXsyevjSetTolerance(st->jacobi, 1e-15));
+    SCFB_SOLVER(h, cusolverDnXsyevjSetMaxSweeps(st->jacobi, 100));
+    SCFB_SOLVER(h, cusolverDnXsyevjSetSortEig(st->jacobi, 1));
+    SCFB_SOLVER(h, cusolverDnDsygvj_bufferSize(st->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
+                                               CUBLAS_FILL_MODE_LOWER, n, st->T1, n, st->Bw, n, st->eps,
+                                               &st->lwork_j, st->jacobi));
+    SCFB_CUDA(h, alloc(&st->work_j, st->lwork_j > 0 ? st->lwork_j : 1));
+  }
   SCFB_CUDA(h, cudaMemcpyAsync(st->S, overlap, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   SCFB_CUDA(h, cudaMemcpyAsync(st->H, h_core, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -392,9 +408,14 @@ int scfb_scf_roothaan(scfb_handle_t h) {
     double* Cs = st->C + s * n2;
     SCFB_CUDA(h, cudaMemcpyAsync(Cs, st->F + s * n2, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     SCFB_CUDA(h, cudaMemcpyAsync(st->Bw, st->S, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    SCFB_SOLVER(h, cusolverDnDsygvd(st->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
-                                    CUBLAS_FILL_MODE_LOWER, n, Cs, n, st->Bw, n, st->eps + s * n,
-                                    st->work, st->lwork, st->dev_info));
+    if (st->jacobi)
+      SCFB_SOLVER(h, cusolverDnDsygvj(st->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
+                                      CUBLAS_FILL_MODE_LOWER, n, Cs, n, st->Bw, n, st->eps + s * n,
+                                      st->work_j, st->lwork_j, st->dev_info, st->jacobi));
+    else
+      SCFB_SOLVER(h, cusolverDnDsygvd(st->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
+                                      CUBLAS_FILL_MODE_LOWER, n, Cs, n, st->Bw, n, st->eps + s * n,
+                                      st->work, st->lwork, st->dev_info));
     h->launches += 1;
   }
   int info = 0;

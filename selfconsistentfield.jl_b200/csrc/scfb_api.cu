@@ -20,11 +20,31 @@ int check_handle(scfb_handle_s* h) {
   return SCFB_OK;
 }
 
-// stage the caller's host arrays into pinned memory and push them with one H2D copy
-// staging layout (host and device): [density 2n^2 | total n^2 | out 2n^2]
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();  // unregistered host memory on old drivers: clear the sticky error
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Push the caller's host arrays to the device staging block [density 2n^2 | total n^2 | out 2n^2].
+// Page-locked caller buffers are copied straight from where they are; pageable ones go through
+// the handle's pinned staging buffer (one memcpy + one H2D copy).
 int stage_inputs(scfb_handle_s* h, int n_spin, const double* density, const double* total,
                  const double* out) {
   const size_t n2 = (size_t)h->n * h->n;
+  if (is_pinned(density) && is_pinned(total) && (!out || is_pinned(out))) {
+    SCFB_CUDA(h, cudaMemcpyAsync(h->d_density, density, n2 * n_spin * sizeof(double),
+                                 cudaMemcpyHostToDevice, h->stream));
+    SCFB_CUDA(h, cudaMemcpyAsync(h->d_total, total, n2 * sizeof(double), cudaMemcpyHostToDevice,
+                                 h->stream));
+    if (out)
+      SCFB_CUDA(h, cudaMemcpyAsync(h->d_out, out, n2 * n_spin * sizeof(double),
+                                   cudaMemcpyHostToDevice, h->stream));
+    return SCFB_OK;
+  }
   std::memcpy(h->h_stage, density, n2 * n_spin * sizeof(double));
   std::memcpy(h->h_stage + 2 * n2, total, n2 * sizeof(double));
   size_t count = 3 * n2;
@@ -294,6 +314,12 @@ int scfb_fock_jk(scfb_handle_t h, int n_spin, const double* density, const doubl
   if (int rc = stage_inputs(h, n_spin, density, total_density, out)) return rc;
   if (int rc = scfb_fock_jk_dev(h, n_spin, h->d_density, h->d_total, h->d_out)) return rc;
   const size_t n2 = (size_t)h->n * h->n;
+  if (is_pinned(out)) {
+    SCFB_CUDA(h, cudaMemcpyAsync(out, h->d_out, n2 * n_spin * sizeof(double), cudaMemcpyDeviceToHost,
+                                 h->stream));
+    SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return SCFB_OK;
+  }
   SCFB_CUDA(h, cudaMemcpyAsync(h->h_stage + 3 * n2, h->d_out, n2 * n_spin * sizeof(double),
                                cudaMemcpyDeviceToHost, h->stream));
   SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
