@@ -20,6 +20,11 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:
+    # the CPU arm may use every host thread; torchrun exports OMP_NUM_THREADS=1 to its workers
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(_v, None)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -57,6 +62,16 @@ def workload_name(a):
     spin = "UHF" if a.n_spin == 2 else "RHF"
     return (f"synthetic {spin} n_bf={a.n_bas}, {a.layout} fp64 ERI "
             f"({eri_total_bytes(a) / 1e9:.2f} GB), hash family")
+
+
+def measured_traffic(a, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
+    committed `ncu --set full` capture of this exact workload (profiles/r01_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path) or world != 1:
+        return None
+    key = f"{a.layout}_n{a.n_bas}_spin{a.n_spin}"
+    return json.load(open(path)).get(key, {}).get("dram_bytes_per_launch")
 
 
 def peaks():
@@ -308,7 +323,7 @@ def run_ours(a, rank, local_rank, world):
                        "layout": a.layout, "sharding": f"{'nu-slabs' if a.layout == 'full' else 'i-blocks'} over {world} rank(s)",
                        "l2_policy": "inputs (ERI shard) far larger than the 126 MB L2; no flush"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": measured_traffic(a, world),
                          "kernel": "jk_full_stream_kernel" if a.layout == "full" else "jk_packed_kernel",
                          "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": launch_bytes, "peak_source": peak_src,

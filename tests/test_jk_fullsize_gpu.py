@@ -75,3 +75,63 @@ def test_rhf_and_uhf_share_one_pass_results(builder):
     assert np.array_equal(out[:, :, 0], j1 - k1[:, :, 0])
     j3, k3 = builder.jk(da[:, :, None], 2 * da)
     assert np.array_equal(j1, j3) and np.array_equal(k1, k3)      # deterministic
+
+
+# ---- BASELINE.json config 4 at full size: RHF n_bf=384, 8-fold packed (21.9 GB) ------------------
+N4 = 384
+
+
+@pytest.fixture(scope="module")
+def packed_builder():
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 30e9:
+        pytest.skip("needs 30 GB of free HBM")
+    b = scf_b200.JKBuilderCUDA.synthetic(N4, "hash", synth.SEED_ERI, layout="packed8")
+    assert b.eri_bytes == 8 * synth.packed8_total(N4)
+    yield b
+    b.close()
+
+
+def sym_unit(n, a, c):
+    m = np.zeros((n, n))
+    m[a, c] = 1.0
+    m[c, a] = 1.0
+    return m
+
+
+def test_packed_fullsize_unit_density_known_answers(packed_builder):
+    """Symmetric unit densities E_ab + E_ba pick 1-2 tensor elements per output entry:
+    J[c,v] = w (ab|cv), K[m,v] = (mb|av) + (ma|bv) with closed-form hash values."""
+    b = packed_builder
+    idx = np.arange(N4)
+    e = synth.hash_eri_elements
+    for (a0, b0), (a1, b1) in [((3, 380), (200, 17)), ((383, 383), (0, 0)), ((128, 127), (5, 5))]:
+        j, k = b.jk(sym_unit(N4, a1, b1)[:, :, None], sym_unit(N4, a0, b0))
+        w0 = 1.0 if a0 == b0 else 2.0
+        jr = w0 * e(a0, b0, idx[:, None], idx[None, :])
+        kr = e(idx[:, None], b1, a1, idx[None, :])
+        if a1 != b1:
+            kr = kr + e(idx[:, None], a1, b1, idx[None, :])
+        assert np.abs(j - jr).max() <= 4e-16 * np.abs(jr).max()
+        assert np.abs(k[:, :, 0] - kr).max() <= 4e-16 * np.abs(kr).max()
+
+
+def test_packed_fullsize_properties(packed_builder):
+    b = packed_builder
+    da = synth.hash_symmetric_matrix(N4, synth.SEED_DA)
+    w = synth.hash_symmetric_matrix(N4, 99)
+    j1, k1 = b.jk(da[:, :, None], 2 * da)
+    jw, kw = b.jk(w[:, :, None], w)
+    assert np.abs(j1 - j1.T).max() < 1e-12 * np.abs(j1).max()
+    assert np.abs(k1[:, :, 0] - k1[:, :, 0].T).max() < 1e-12 * np.abs(k1).max()
+    scale = np.abs(j1).max() * np.abs(w).sum()
+    assert abs(np.sum(w * j1) - np.sum(2 * da * jw)) < 1e-12 * scale       # reciprocity
+    assert abs(np.sum(w * k1[:, :, 0]) - np.sum(da * kw[:, :, 0])) < 1e-12 * scale
+    j2, k2 = b.jk((da + 0.5 * w)[:, :, None], 2 * da + 3 * w)               # linearity
+    assert np.abs(j2 - (j1 + 3 * jw)).max() < 1e-12 * np.abs(j2).max()
+    assert np.abs(k2[:, :, 0] - (k1[:, :, 0] + 0.5 * kw[:, :, 0])).max() < 1e-12 * np.abs(k2).max()
+    # run-to-run: fp64 RED order is not fixed, results agree far inside the 1e-12 gate
+    j3, k3 = b.jk(da[:, :, None], 2 * da)
+    assert np.abs(j3 - j1).max() < 1e-13 * np.abs(j1).max()
+    assert np.abs(k3 - k1).max() < 1e-13 * np.abs(k1).max()
