@@ -34,7 +34,13 @@
 
 namespace {
 
-constexpr int LB = 128;  // threads per CTA = 4 independent warps, 256 l values
+// One warp per CTA: the warps of an item never cooperate, and in the triangular iteration space
+// multi-warp CTAs keep dead warps' slots (and their shared memory) pinned until the longest
+// warp finishes; with LB = 32 every resident CTA is a live warp (measured 5.6 -> 4.9 ms).
+#ifndef SCFB_LB
+#define SCFB_LB 32
+#endif
+constexpr int LB = SCFB_LB;  // threads per CTA = LB/32 independent warps, 2*LB l values
 
 __host__ __device__ __forceinline__ uint64_t tri(uint64_t i) { return i * (i + 1) / 2; }
 __host__ __device__ __forceinline__ uint64_t seg_off(uint64_t k) { return tri(k) + (k + 1) / 2; }
@@ -856,12 +862,14 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
           h->eri, h->pk_btab, h->pk_offset, h->pk_dpad, dstride, h->pk_dq2, Kp, Jp, n, h->i_lo); \
     }                                                                                           \
   } while (0)
-    if (n_spin == 1 && kc == 8) SCFB_PK_LAUNCH(1, 8, 2);
-    else if (n_spin == 1 && minb_sel == 3) SCFB_PK_LAUNCH(1, 4, 3);
-    else if (n_spin == 1 && minb_sel == 2) SCFB_PK_LAUNCH(1, 4, 2);
-    else if (n_spin == 1) SCFB_PK_LAUNCH(1, 4, 4);
-    else if (kc == 8) SCFB_PK_LAUNCH(2, 8, 2);
-    else SCFB_PK_LAUNCH(2, 4, 3);
+    // resident CTAs per SM targeted by __launch_bounds__ (register cap = 65536 / (LB * MINB))
+    constexpr int W = 128 / LB;  // CTAs per 128 threads
+    (void)minb_sel;
+    if (n_spin == 1 && kc == 8) SCFB_PK_LAUNCH(1, 8, 2 * W);
+    else if (n_spin == 1 && minb_sel == 4) SCFB_PK_LAUNCH(1, 4, 4 * W);
+    else if (n_spin == 1) SCFB_PK_LAUNCH(1, 4, 3 * W);
+    else if (kc == 8) SCFB_PK_LAUNCH(2, 8, 2 * W);
+    else SCFB_PK_LAUNCH(2, 4, 3 * W);
 #undef SCFB_PK_LAUNCH
     e = cudaGetLastError();
     if (e != cudaSuccess)
