@@ -113,17 +113,17 @@ template <int VEC, int NSPIN, bool FULL>
 __device__ __forceinline__ void stream_rows(const double* __restrict__ xbase,
                                             const double* __restrict__ dtot,
                                             const double* __restrict__ dens, int n, size_t n2,
-                                            int a0, int c0, int tcn, int g, int G,
+                                            int a0, int c0, int tcn, int g, int G, int b_lo, int b_hi,
                                             double (&jacc)[TC], double (&kacc)[NSPIN][VEC]) {
   Vec<VEC> xc[TC], xn[TC];
   Vec<VEC> dtc, dtn;
-  int b = g;
-  if (b >= n) return;
+  int b = b_lo + g;
+  if (b >= b_hi) return;
   load_row<VEC, FULL>(xc, xbase + (size_t)b * n, n2, tcn);
   dtc.load_cached(dtot + (size_t)b * n + a0);
-  for (; b < n; b += G) {
+  for (; b < b_hi; b += G) {
     const int bn = b + G;
-    if (bn < n) {  // prefetch the next row this group owns while the FMAs below run
+    if (bn < b_hi) {  // prefetch the next row this group owns while the FMAs below run
       load_row<VEC, FULL>(xn, xbase + (size_t)bn * n, n2, tcn);
       dtn.load_cached(dtot + (size_t)bn * n + a0);
     }
@@ -134,13 +134,16 @@ __device__ __forceinline__ void stream_rows(const double* __restrict__ xbase,
   }
 }
 
-// grid = (n_chunks, n_slabs); block = roundup32(R*G) threads; dynamic smem = kred.
+// grid = (n_chunks, n_slabs, BS); block = roundup32(R*G) threads; dynamic smem = kred.
 // MAXT = 256 (2 CTAs/SM) covers rows of up to 512 doubles; MAXT = 512 (1 CTA/SM) rows up to 1024.
+// BS = gridDim.z > 1 splits the b range of a work item over BS CTAs (used when a shard has too
+// few equal-size items to fill the SMs evenly): J then also becomes a per-CTA partial (jpart).
 template <int VEC, int NSPIN, int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 2 : 1)
 jk_full_stream_kernel(const double* __restrict__ eri, const double* __restrict__ dtot,
                       const double* __restrict__ dens, double* __restrict__ jk,
-                      double* __restrict__ kpart, int n, int nu_lo, int R, int G) {
+                      double* __restrict__ kpart, double* __restrict__ jpart, int n, int nu_lo,
+                      int R, int G) {
   extern __shared__ double kred[];  // [G][NSPIN][n] when G > 1
   __shared__ double jred[MAXT / 32][TC];
 
@@ -155,6 +158,9 @@ jk_full_stream_kernel(const double* __restrict__ eri, const double* __restrict__
   const int c0 = chunk * TC;
   const int tcn = min(TC, n - c0);
   const size_t n2 = (size_t)n * n;
+  const int BS = gridDim.z, bz = blockIdx.z;
+  const int nb = (n + BS - 1) / BS;
+  const int b_lo = bz * nb, b_hi = min(n, b_lo + nb);
 
   double jacc[TC];
   double kacc[NSPIN][VEC];
@@ -168,9 +174,9 @@ jk_full_stream_kernel(const double* __restrict__ eri, const double* __restrict__
   if (active) {
     const double* xbase = eri + ((size_t)slab * n + c0) * n2 + a0;
     if (tcn == TC)
-      stream_rows<VEC, NSPIN, true>(xbase, dtot, dens, n, n2, a0, c0, tcn, g, G, jacc, kacc);
+      stream_rows<VEC, NSPIN, true>(xbase, dtot, dens, n, n2, a0, c0, tcn, g, G, b_lo, b_hi, jacc, kacc);
     else
-      stream_rows<VEC, NSPIN, false>(xbase, dtot, dens, n, n2, a0, c0, tcn, g, G, jacc, kacc);
+      stream_rows<VEC, NSPIN, false>(xbase, dtot, dens, n, n2, a0, c0, tcn, g, G, b_lo, b_hi, jacc, kacc);
   }
 
   // ---- J[c0+t, nu]: reduce over every thread of the CTA (all a, all b) ----
@@ -189,12 +195,16 @@ jk_full_stream_kernel(const double* __restrict__ eri, const double* __restrict__
   }
   __syncthreads();
   const int n_warps = (blockDim.x + 31) >> 5;
+  const size_t item = ((size_t)slab * n_chunks + chunk) * BS + bz;
   if (tid < tcn) {
     double v = 0.0;
     for (int w = 0; w < n_warps; ++w) v += jred[w][tid];
-    jk[(size_t)(nu_lo + slab) * n + c0 + tid] = v;
+    if (BS == 1)
+      jk[(size_t)(nu_lo + slab) * n + c0 + tid] = v;
+    else
+      jpart[item * TC + tid] = v;
   }
-  double* kp = kpart + ((size_t)slab * n_chunks + chunk) * NSPIN * n;
+  double* kp = kpart + item * NSPIN * n;
   if (G > 1) {
     for (int i = tid; i < NSPIN * n; i += blockDim.x) {
       double v = 0.0;
@@ -209,20 +219,29 @@ jk_full_stream_kernel(const double* __restrict__ eri, const double* __restrict__
   }
 }
 
-// K[a, nu, s] = sum over chunks of the partial rows, fixed order -> deterministic.
-__global__ void k_reduce_kernel(const double* __restrict__ kpart, double* __restrict__ jk, int n,
-                                int nu_lo, int n_slabs, int n_chunks, int n_spin) {
+// K[a, nu, s] = sum over (chunk, b-split) of the partial rows; with b-splits also
+// J[c, nu] = sum over the b-splits.  Fixed order -> deterministic.
+__global__ void k_reduce_kernel(const double* __restrict__ kpart, const double* __restrict__ jpart,
+                                double* __restrict__ jk, int n, int nu_lo, int n_slabs,
+                                int n_chunks, int n_spin, int bs) {
   const size_t total = (size_t)n * n_slabs * n_spin;
+  const size_t parts = (size_t)n_chunks * bs;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const int a = (int)(i % n);
     const size_t rest = i / n;
     const int slab = (int)(rest % n_slabs);
     const int s = (int)(rest / n_slabs);
-    const double* p = kpart + (((size_t)slab * n_chunks) * n_spin + s) * n + a;
+    const double* p = kpart + (((size_t)slab * parts) * n_spin + s) * n + a;
     double v = 0.0;
-    for (int c = 0; c < n_chunks; ++c) v += p[(size_t)c * n_spin * n];
+    for (size_t c = 0; c < parts; ++c) v += p[c * n_spin * n];
     jk[(size_t)(1 + s) * n * n + (size_t)(nu_lo + slab) * n + a] = v;
+    if (bs > 1 && s == 0) {  // this thread also owns J[c = a, nu]
+      const double* q = jpart + (((size_t)slab * n_chunks + a / TC) * bs) * TC + a % TC;
+      double j = 0.0;
+      for (int z = 0; z < bs; ++z) j += q[(size_t)z * TC];
+      jk[(size_t)(nu_lo + slab) * n + a] = j;
+    }
   }
 }
 
@@ -248,17 +267,32 @@ cudaError_t launch_stream(scfb_handle_s* h, const double* d_density, const doubl
   if (G > n) G = n;
   const int threads = ((R * G + 31) / 32) * 32;
   const size_t smem = G > 1 ? (size_t)G * NSPIN * n * sizeof(double) : 0;
-  dim3 grid(n_chunks, n_slabs);
+  dim3 grid(n_chunks, n_slabs, h->b_splits);
   jk_full_stream_kernel<VEC, NSPIN, MAXT><<<grid, threads, smem, h->stream>>>(
-      h->eri, d_total, d_density, h->jk, h->kpart, n, h->nu_lo, R, G);
+      h->eri, d_total, d_density, h->jk, h->kpart, h->jpart, n, h->nu_lo, R, G);
   return cudaGetLastError();
 }
 
 }  // namespace
 
+// b-splits: equal-size work items fill 2 x 148 resident CTA slots in waves; below ~4 waves the
+// last, partly filled wave costs > 10 % (n_bf = 256 over 8 GPUs: 1024 items = 3.46 -> 4 waves).
+int scfb_full_b_splits(int n, int n_slabs) {
+  const long items = (long)((n + TC - 1) / TC) * n_slabs;
+  if (items <= 0) return 1;
+  int bs = 1;
+  while (bs < 4 && items * bs < 4L * 2 * 148 && n / (2 * bs) >= 16) bs *= 2;
+  return bs;
+}
+
 uint64_t scfb_kpart_elems_full(int n, int n_slabs) {
   const uint64_t n_chunks = (n + TC - 1) / TC;
-  return (uint64_t)n_slabs * n_chunks * 2 * n;
+  return (uint64_t)n_slabs * n_chunks * scfb_full_b_splits(n, n_slabs) * 2 * n;
+}
+
+uint64_t scfb_jpart_elems_full(int n, int n_slabs) {
+  const uint64_t n_chunks = (n + TC - 1) / TC;
+  return (uint64_t)n_slabs * n_chunks * scfb_full_b_splits(n, n_slabs) * TC;
 }
 
 int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
@@ -295,8 +329,8 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
   const size_t total = (size_t)n * n_slabs * n_spin;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k_reduce_kernel<<<blocks, 256, 0, h->stream>>>(h->kpart, h->jk, n, h->nu_lo, n_slabs, n_chunks,
-                                                 n_spin);
+  k_reduce_kernel<<<blocks, 256, 0, h->stream>>>(h->kpart, h->jpart, h->jk, n, h->nu_lo, n_slabs,
+                                                 n_chunks, n_spin, h->b_splits);
   e = cudaGetLastError();
   if (e != cudaSuccess)
     return scfb_fail(h, SCFB_ERR_CUDA, "k_reduce_kernel launch: %s", cudaGetErrorString(e));

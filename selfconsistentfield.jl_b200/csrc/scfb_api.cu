@@ -110,6 +110,7 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
     scfb_split_range(n_bas, rank, n_ranks, &h->nu_lo, &h->nu_hi);
     h->eri_elems = n2 * n * (uint64_t)(h->nu_hi - h->nu_lo);
     h->kpart_elems = scfb_kpart_elems_full(n_bas, h->nu_hi - h->nu_lo);
+    h->b_splits = scfb_full_b_splits(n_bas, h->nu_hi - h->nu_lo);
   } else {
     scfb_packed_split(n_bas, rank, n_ranks, &h->i_lo, &h->i_hi);
     h->pk_offset = scfb_packed_offset(h->i_lo);
@@ -140,6 +141,8 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
   h->jk_sum = h->jk;
   if (n_ranks > 1) CREATE_CUDA(cudaMalloc(&h->jk_sum, 3 * n2 * sizeof(double)));
   if (h->kpart_elems) CREATE_CUDA(cudaMalloc(&h->kpart, h->kpart_elems * sizeof(double)));
+  if (layout == SCFB_LAYOUT_FULL && h->b_splits > 1)
+    CREATE_CUDA(cudaMalloc(&h->jpart, scfb_jpart_elems_full(n_bas, h->nu_hi - h->nu_lo) * sizeof(double)));
   if (layout == SCFB_LAYOUT_PACKED8) {
     const uint64_t PQ = scfb_packed_dq_elems(n_bas);
     CREATE_CUDA(cudaMalloc(&h->pk_acc, (PQ + 2 * (n2 + 64)) * sizeof(double)));
@@ -169,6 +172,7 @@ int scfb_destroy(scfb_handle_t h) {
   if (h->jk_sum != h->jk) cudaFree(h->jk_sum);
   cudaFree(h->jk);
   cudaFree(h->kpart);
+  cudaFree(h->jpart);
   cudaFree(h->pk_acc);
   cudaFree(h->pk_dq2);
   cudaFree(h->pk_dpad);

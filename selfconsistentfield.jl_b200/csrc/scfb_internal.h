@@ -36,7 +36,9 @@ struct scfb_handle_s {
   double* d_out = nullptr;      // n*n*2
   double* jk = nullptr;         // [J | K_0 | K_1], 3*n*n, this rank's partial: zero outside owned columns
   double* jk_sum = nullptr;     // allreduce result (n_ranks > 1); == jk when single rank
-  double* kpart = nullptr;      // per-(nu, c-chunk) partial K rows
+  double* kpart = nullptr;      // per-(nu, c-chunk, b-split) partial K rows
+  double* jpart = nullptr;      // per-(nu, c-chunk, b-split) partial J values (b_splits > 1)
+  int b_splits = 1;             // CTAs sharing one (nu, c-chunk) work item along b
   uint64_t kpart_elems = 0;
   double* h_stage = nullptr;    // pinned host staging, 5*n*n
 
@@ -95,6 +97,8 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
                         const double* d_total);            // fills h->jk for owned columns
 int scfb_launch_accumulate(scfb_handle_s* h, int n_spin, const double* d_jk, double* d_out);  // out += J - K_s
 uint64_t scfb_kpart_elems_full(int n, int n_slabs);
+uint64_t scfb_jpart_elems_full(int n, int n_slabs);
+int scfb_full_b_splits(int n, int n_slabs);
 // jk_packed.cu
 void scfb_packed_split(int n, int rank, int n_ranks, int* i_lo, int* i_hi);
 uint64_t scfb_packed_offset(int i);
