@@ -48,6 +48,8 @@ def parse():
     p.add_argument("--cpu-steps", type=int, default=3)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
+    p.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
+                   help="cross-GPU sum of the partial J/K: NCCL allreduce or peer-memory stores")
     return p.parse_args()
 
 
@@ -228,7 +230,10 @@ def run_ours(a, rank, local_rank, world):
     n2 = n * n
     builder = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synthetic.SEED_ERI, layout=a.layout,
                                                device=local_rank, rank=rank, n_ranks=world)
-    if world > 1:
+    if world > 1 and a.exchange == "p2p":
+        builder.peer_import(scf_b200.distributed.exchange_peer_handles(dist, builder))
+        dist.barrier()
+    elif world > 1:
         builder.comm_init(comm_id)
     stream = torch.cuda.Stream()
     builder.set_stream(stream.cuda_stream)
@@ -321,6 +326,7 @@ def run_ours(a, rank, local_rank, world):
             "data": "synthetic",
             "config": {"workload": workload_name(a), "n_bas": n, "n_spin": n_spin,
                        "layout": a.layout, "sharding": f"{'nu-slabs' if a.layout == 'full' else 'i-blocks'} over {world} rank(s)",
+                       "exchange": a.exchange if world > 1 else "none",
                        "l2_policy": "inputs (ERI shard) far larger than the 126 MB L2; no flush"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic(a, world),

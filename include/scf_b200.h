@@ -149,6 +149,14 @@ int scfb_sygvd(scfb_handle_t h, int n_spin, int n_orb, const double* fock, const
  * means (torch.distributed / MPI / a file); every rank then calls scfb_comm_init. */
 int scfb_comm_unique_id(char* id128);
 int scfb_comm_init(scfb_handle_t h, const char* id128);
+/* Opt-in alternative exchange over peer memory (all ranks on one NVSwitch box, <= 8): every rank
+ * calls scfb_peer_export (128 bytes of CUDA IPC handles), the host gathers the n_ranks x 128
+ * bytes in rank order, every rank calls scfb_peer_import.  Builds then store their partial J/K
+ * straight into every peer's receive area and sum the slots locally (deterministic order)
+ * instead of calling ncclAllReduce.  A rank that never arrives makes the wait time out
+ * (SCFB_ERR_NCCL at the next synchronising call) instead of hanging. */
+int scfb_peer_export(scfb_handle_t h, char* handle128);
+int scfb_peer_import(scfb_handle_t h, const char* all_handles);
 
 #ifdef __cplusplus
 }

@@ -158,6 +158,15 @@ class JKBuilderCUDA(TwoElectronBuilder):
     def sync(self):
         capi.check(capi.lib().scfb_sync(self._h), self._h)
 
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        capi.check(capi.lib().scfb_peer_export(self._h, buf), self._h)
+        return buf.raw
+
+    def peer_import(self, all_handles: bytes):
+        assert len(all_handles) == 128 * self.n_ranks
+        capi.check(capi.lib().scfb_peer_import(self._h, all_handles), self._h)
+
     def comm_init(self, id128: bytes):
         capi.check(capi.lib().scfb_comm_init(self._h, id128), self._h)
 

@@ -67,6 +67,8 @@ _SIGNATURES = {
     "scfb_sygvd": [_h, C.c_int, C.c_int, _dp, _dp, _dp, _dp],
     "scfb_comm_unique_id": [C.c_char_p],
     "scfb_comm_init": [_h, C.c_char_p],
+    "scfb_peer_export": [_h, C.c_char_p],
+    "scfb_peer_import": [_h, C.c_char_p],
 }
 _RESTYPE = {"scfb_last_error": C.c_char_p}
 

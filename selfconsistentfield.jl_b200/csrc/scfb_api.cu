@@ -165,6 +165,7 @@ int scfb_destroy(scfb_handle_t h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   scfb_comm_destroy(h);
+  scfb_peer_destroy(h);
   scfb_scf_free(h);
   scfb_dense_handles_destroy(h);
   cudaFree(h->eri);
@@ -188,7 +189,7 @@ int scfb_destroy(scfb_handle_t h) {
 int scfb_sync(scfb_handle_t h) {
   if (int rc = check_handle(h)) return rc;
   SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
-  return SCFB_OK;
+  return scfb_peer_check(h);
 }
 
 int scfb_set_stream(scfb_handle_t h, void* cuda_stream) {
@@ -301,12 +302,17 @@ int scfb_fock_jk_dev(scfb_handle_t h, int n_spin, const double* d_density,
   if (int rc = check_build_args(h, n_spin, d_density, d_total_density, d_out)) return rc;
   if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
   if (int rc = launch_jk(h, n_spin, d_density, d_total_density)) return rc;
-  const double* jk_final = h->jk;
-  if (h->n_ranks > 1 && h->nccl_comm) {
-    if (int rc = scfb_comm_allreduce_jk(h, n_spin)) return rc;
-    jk_final = h->jk_sum;
+  if (h->n_ranks > 1 && scfb_peer_ready(h)) {
+    // peer-memory exchange: send to every peer, then wait + sum + accumulate in one kernel
+    if (int rc = scfb_peer_exchange(h, n_spin, d_out)) return rc;
+  } else {
+    const double* jk_final = h->jk;
+    if (h->n_ranks > 1 && h->nccl_comm) {
+      if (int rc = scfb_comm_allreduce_jk(h, n_spin)) return rc;
+      jk_final = h->jk_sum;
+    }
+    if (int rc = scfb_launch_accumulate(h, n_spin, jk_final, d_out)) return rc;
   }
-  if (int rc = scfb_launch_accumulate(h, n_spin, jk_final, d_out)) return rc;
   if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
   return SCFB_OK;
 }
@@ -322,13 +328,13 @@ int scfb_fock_jk(scfb_handle_t h, int n_spin, const double* density, const doubl
     SCFB_CUDA(h, cudaMemcpyAsync(out, h->d_out, n2 * n_spin * sizeof(double), cudaMemcpyDeviceToHost,
                                  h->stream));
     SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
-    return SCFB_OK;
+    return scfb_peer_check(h);
   }
   SCFB_CUDA(h, cudaMemcpyAsync(h->h_stage + 3 * n2, h->d_out, n2 * n_spin * sizeof(double),
                                cudaMemcpyDeviceToHost, h->stream));
   SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
   std::memcpy(out, h->h_stage + 3 * n2, n2 * n_spin * sizeof(double));
-  return SCFB_OK;
+  return scfb_peer_check(h);
 }
 
 int scfb_jk_split(scfb_handle_t h, int n_spin, const double* density, const double* total_density,
@@ -340,7 +346,10 @@ int scfb_jk_split(scfb_handle_t h, int n_spin, const double* density, const doub
   if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
   if (int rc = launch_jk(h, n_spin, h->d_density, h->d_total)) return rc;
   const double* jk_final = h->jk;
-  if (h->n_ranks > 1 && h->nccl_comm) {
+  if (h->n_ranks > 1 && scfb_peer_ready(h)) {
+    if (int rc = scfb_peer_exchange(h, n_spin, nullptr)) return rc;
+    jk_final = h->jk_sum;
+  } else if (h->n_ranks > 1 && h->nccl_comm) {
     if (int rc = scfb_comm_allreduce_jk(h, n_spin)) return rc;
     jk_final = h->jk_sum;
   }
@@ -351,7 +360,7 @@ int scfb_jk_split(scfb_handle_t h, int n_spin, const double* density, const doub
   SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
   std::memcpy(J, h->h_stage, n2 * sizeof(double));
   std::memcpy(K, h->h_stage + n2, n2 * n_spin * sizeof(double));
-  return SCFB_OK;
+  return scfb_peer_check(h);
 }
 
 int scfb_last_build_ms(scfb_handle_t h, double* stream_ms, double* total_ms) {

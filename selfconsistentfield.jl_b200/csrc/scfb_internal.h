@@ -52,6 +52,7 @@ struct scfb_handle_s {
   void* blas = nullptr;           // cublasHandle_t, created on first use
   void* solver = nullptr;         // cusolverDnHandle_t, created on first use
 
+  void* peer = nullptr;       // PeerState (peer.cu) when the peer-memory exchange is set up
   void* nccl_comm = nullptr;  // ncclComm_t when n_ranks > 1 and initialised
 
   char err[512] = {0};
@@ -115,3 +116,8 @@ int scfb_comm_destroy(scfb_handle_s* h);
 // dense.cu
 void scfb_scf_free(scfb_handle_s* h);
 void scfb_dense_handles_destroy(scfb_handle_s* h);
+// peer.cu
+bool scfb_peer_ready(scfb_handle_s* h);
+void scfb_peer_destroy(scfb_handle_s* h);
+int scfb_peer_exchange(scfb_handle_s* h, int n_spin, double* d_out);  // d_out == nullptr: fill jk_sum
+int scfb_peer_check(scfb_handle_s* h);

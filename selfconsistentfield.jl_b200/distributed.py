@@ -34,13 +34,30 @@ def exchange_comm_id(dist, rank: int, make_id=None) -> bytes:
     return bytes(cid)
 
 
-def sharded_builder(factory, dist=None, **kw):
+def exchange_peer_handles(dist, builder) -> bytes:
+    """All-gather the 128-byte CUDA IPC handle records of every rank (rank order)."""
+    mine = builder.peer_export()
+    box = [None] * dist.get_world_size()
+    dist.all_gather_object(box, mine)
+    if any(not isinstance(x, (bytes, bytearray)) or len(x) != 128 for x in box):
+        raise RuntimeError("peer handle exchange failed")
+    return b"".join(bytes(x) for x in box)
+
+
+def sharded_builder(factory, dist=None, exchange="nccl", **kw):
     """Create this rank's builder with `factory(rank=..., n_ranks=..., device=..., **kw)`
-    (e.g. JKBuilderCUDA.synthetic / .from_tensor partial) and join the communicator."""
+    (e.g. JKBuilderCUDA.synthetic / .from_tensor partial) and set up the cross-GPU exchange:
+    "nccl" (one ncclAllReduce per build, the default) or "p2p" (peer-memory stores + local sum)."""
     rank, local_rank, world = env_ranks()
     b = factory(rank=rank, n_ranks=world, device=local_rank, **kw)
     if world > 1:
         if dist is None:
             raise ValueError("torch.distributed module required for world_size > 1")
-        b.comm_init(exchange_comm_id(dist, rank))
+        if exchange == "p2p":
+            b.peer_import(exchange_peer_handles(dist, b))
+            dist.barrier()          # nobody stores into a peer before everyone has mapped it
+        elif exchange == "nccl":
+            b.comm_init(exchange_comm_id(dist, rank))
+        else:
+            raise ValueError(f"unknown exchange {exchange!r}")
     return b

@@ -22,10 +22,14 @@ def main():
     rank, local_rank, world = scf_b200.distributed.env_ranks()
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    for n, n_spin in ((10, 1), (33, 2), (64, 2)):
+    exchange = sys.argv[1] if len(sys.argv) > 1 else "nccl"
+    for n, n_spin, layout in ((10, 1, "full"), (33, 2, "full"), (64, 2, "full"), (40, 2, "packed8"),
+                              (7, 1, "full")):
         b = scf_b200.distributed.sharded_builder(
-            lambda **kw: scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, **kw), dist)
-        assert b.shard_range == scf_b200.distributed.shard_range(n, rank, world)
+            lambda **kw: scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, layout=layout, **kw),
+            dist, exchange=exchange)
+        if layout == "full":
+            assert b.shard_range == scf_b200.distributed.shard_range(n, rank, world)
         eri = synth.hash_eri(n)
         da = synth.hash_symmetric_matrix(n, synth.SEED_DA)
         db = synth.hash_symmetric_matrix(n, synth.SEED_DB)
@@ -39,15 +43,33 @@ def main():
         b.add_2e_term(out, dens, total)
         ref = o.add_2e_term_exact(np.zeros((n, n, n_spin)), eri, dens, total)
         assert np.abs(out - ref).max() < 1e-12 * np.abs(ref).max()
-        # identical on every rank (bitwise: same partials, same NCCL reduction result)
+        for _ in range(5):      # repeated builds: epochs / double buffering / partial-buffer hygiene
+            out2 = np.zeros((n, n, n_spin), order="F")
+            b.add_2e_term(out2, dens, total)
+            assert np.abs(out2 - ref).max() < 1e-12 * np.abs(ref).max()
+        # identical on every rank (full layout: bitwise, same partials and same reduction order)
         t = torch.from_numpy(np.ascontiguousarray(out)).cuda()
         gathered = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(gathered, t)
-        assert all(torch.equal(g, gathered[0]) for g in gathered)
+        if layout == "full":
+            assert all(torch.equal(g, gathered[0]) for g in gathered)
         b.close()
+    # BASELINE-size shard set: n_bf = 256 UHF split over the ranks, exact unit-density answers
+    n = 256
+    b = scf_b200.distributed.sharded_builder(
+        lambda **kw: scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, **kw), dist,
+        exchange=exchange)
+    idx = np.arange(n)
+    unit = scf_b200.synthetic.unit_symmetric
+    j, k = b.jk(np.stack([unit(n, 17, 5), unit(n, 255, 255)], axis=2), unit(n, 3, 250))
+    e = synth.hash_eri_elements
+    assert np.array_equal(j, 2 * e(3, 250, idx[:, None], idx[None, :]))
+    assert np.array_equal(k[:, :, 0], e(idx[:, None], 5, 17, idx[None, :]) + e(idx[:, None], 17, 5, idx[None, :]))
+    assert np.array_equal(k[:, :, 1], e(idx[:, None], 255, 255, idx[None, :]))
+    b.close()
     dist.barrier()
     if rank == 0:
-        print(f"mgpu_check ok: world={world}")
+        print(f"mgpu_check ok: world={world} exchange={exchange}")
     dist.destroy_process_group()
 
 
