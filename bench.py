@@ -165,11 +165,24 @@ def cpu_reference_sample(n, n_spin, n_slabs, steps):
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count()
+    # extra reference point (clearly NOT what the reference does): a single-pass OpenMP C kernel
+    onepass = None
+    try:
+        from oracle import c_oracle
+        density = np.asfortranarray(np.stack(dens, axis=2))
+        tt = []
+        for _ in range(steps + 1):
+            t0 = time.perf_counter()
+            c_oracle.jk_onepass(eri, density, total, 0, n_slabs)
+            tt.append(time.perf_counter() - t0)
+        onepass = 1.0 / (float(np.median(tt[1:])) * n / n_slabs)
+    except Exception:                                                 # pragma: no cover
+        pass
     return {"value": 1.0 / (t * n / n_slabs), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n_slabs} of {n} nu-slabs of the same n_bf={n} hash tensor "
                       f"({8 * n ** 3 * n_slabs / 1e9:.2f} GB), NumPy/OpenBLAS GEMV for J + "
                       f"permute-copy+GEMV per spin for K, median of {steps} passes, scaled x{n}/{n_slabs}",
-            "sample_seconds": t}
+            "sample_seconds": t, "onepass_openmp_c_value": onepass}
 
 
 def run_reference(a, rank):

@@ -137,22 +137,27 @@ def test_chain_generator_matches_host_twin(n):
 # ---- medium sizes against the fp64 oracle ------------------------------------------------
 @pytest.mark.parametrize("n,n_spin", [(64, 1), (64, 2), (96, 2), (100, 1), (127, 2)])
 def test_hash_family_medium(n, n_spin):
-    eri = synth.hash_eri(n)
+    """Arbiter at these sizes: the C restatement with long-double accumulation."""
+    from oracle import c_oracle
+    eri = c_oracle.hash_eri(n, synth.SEED_ERI)
     da = synth.hash_symmetric_matrix(n, synth.SEED_DA)
     db = synth.hash_symmetric_matrix(n, synth.SEED_DB)
     density = np.stack([da, db][:n_spin], axis=2)
     total = 2 * da if n_spin == 1 else da + db
     b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI)
     j, k = b.jk(density, total)
-    n2 = n * n
-    m = eri.reshape(n2, n2, order="F")
-    jr = (m.T @ total.reshape(n2, order="F")).reshape(n, n, order="F")
+    jr, kr = c_oracle.jk_literal_ld(eri, density, total)
     assert rel_err(j, jr) < RTOL
-    for s in range(n_spin):
-        kr = np.einsum("mban,ab->mn", eri, density[:, :, s], optimize=True)
-        assert rel_err(k[:, :, s], kr) < RTOL
+    assert rel_err(k, kr) < RTOL
     # 8-fold symmetric tensor + symmetric D  =>  J and K symmetric
     assert rel_err(j, j.T) < RTOL and rel_err(k[:, :, 0], k[:, :, 0].T) < RTOL
+    # and an unsymmetric density against the literal index patterns
+    rng = np.random.default_rng(n)
+    du = rng.standard_normal((n, n, n_spin))
+    tu = rng.standard_normal((n, n))
+    j, k = b.jk(du, tu)
+    jr, kr = c_oracle.jk_literal_ld(eri, du, tu)
+    assert rel_err(j, jr) < RTOL and rel_err(k, kr) < RTOL
     b.close()
 
 
