@@ -127,6 +127,19 @@ function with_cuda_builder(integrals; kwargs...)
 end
 
 # ---------------------------------------------------------------------------------------
+# Multi-GPU (one Julia process per GPU, e.g. under MPI.jl): rank 0 creates the NCCL id, every
+# rank joins; afterwards add_2e_term! returns the allreduced result on every rank.
+# ---------------------------------------------------------------------------------------
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:scfb_comm_unique_id, libscf), Cint, (Ptr{UInt8},), id))
+    id                                        # ship to the other ranks, e.g. MPI.Bcast!(id, 0, comm)
+end
+
+comm_init!(b::JKBuilderCUDA, id::Vector{UInt8}) =
+    check(ccall((:scfb_comm_init, libscf), Cint, (Ptr{Cvoid}, Ptr{UInt8}), b.handle, id), b.handle)
+
+# ---------------------------------------------------------------------------------------
 # Device-resident SCF step (scfb_scf_*): S, h_core, D, F, error, orbitals and the DIIS history
 # stay in HBM; only scalars, DIIS rows and coefficients cross PCIe.  The caller keeps the
 # control flow of src/run_scf.jl:21-49 and the small solves of cDIIS.jl:33-63 / EDIIS.jl:20-44.
