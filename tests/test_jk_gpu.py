@@ -243,3 +243,34 @@ def test_wide_rows_known_answers_on_a_shard(n, n_ranks):
     j_b, k_b = b.jk((d - d1)[:, :, None], d - d1)
     assert rel_err(j_a + j_b, j_full) < RTOL and rel_err(k_a + k_b, k_full) < RTOL
     b.close()
+
+
+# ---- device-pointer twin on the caller's stream (what bench.py times) ------------------------
+@pytest.mark.parametrize("layout", ["full", "packed8"])
+def test_device_pointer_api_on_callers_stream(layout):
+    import torch
+    n, n_spin = 48, 2
+    da = synth.hash_symmetric_matrix(n, synth.SEED_DA)
+    db = synth.hash_symmetric_matrix(n, synth.SEED_DB)
+    dens = np.asfortranarray(np.stack([da, db], axis=2))
+    total = np.asfortranarray(da + db)
+    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, layout=layout)
+    ref = np.zeros((n, n, n_spin), order="F")
+    b.add_2e_term(ref, dens, total)                       # host-pointer path
+    stream = torch.cuda.Stream()
+    b.set_stream(stream.cuda_stream)
+    # torch tensors viewing column-major arrays: tensor[s, v, m] == array[m, v, s]
+    d_dens = torch.from_numpy(dens.T.copy()).cuda()
+    d_total = torch.from_numpy(total.T.copy()).cuda()
+    d_out = torch.zeros_like(d_dens)
+    before = b.launch_count
+    with torch.cuda.stream(stream):
+        for _ in range(3):                                # accumulates: 3 x (J - K)
+            b.add_2e_term_device(d_out.data_ptr(), d_dens.data_ptr(), d_total.data_ptr(), n_spin)
+    stream.synchronize()
+    assert b.launch_count - before >= 9                   # >= 3 kernels per build
+    out = d_out.cpu().numpy().T
+    assert rel_err(out, 3 * ref) < RTOL
+    stream_ms, total_ms = b.last_build_ms()
+    assert 0 < stream_ms <= total_ms
+    b.close()
