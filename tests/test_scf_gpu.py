@@ -236,3 +236,22 @@ def test_config2_n128_chain_rhf_complete_scf():
     assert abs(res["energies_newest"]["total"] - ref["energies_newest"]["total"]) < 1e-10
     assert abs(res["energies_newest"]["total"] - (-85.2054609659)) < 1e-9
     builder.close()
+
+
+def test_example_driver_config1(golden_dir, tmp_path):
+    """BASELINE.json config 1: the example driver on the bundled Be/3-21G integral dump
+    (examples/HartreeFock.jl -> examples/HartreeFock.py), RHF and UHF."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dump = os.path.join(golden_dir, "integrals_be_3-21g.npz")
+    for flag in ("--restricted", "--unrestricted"):
+        out = tmp_path / f"res{flag}.npz"
+        p = subprocess.run([sys.executable, os.path.join(root, "examples", "HartreeFock.py"), flag, dump,
+                            str(out)], capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout + p.stderr
+        assert "SCF converged." in p.stdout and "virial ratio" in p.stdout
+        line = [ln for ln in p.stdout.splitlines() if "E_total" in ln][0]
+        assert abs(float(line.split("=")[1]) - (-14.4868202421763)) < 1e-9 * 14.49
+        z = np.load(out)
+        assert abs(float(z["energy_coulomb"]) + float(z["energy_exchange"]) - float(z["energy_2e"])) < 1e-6
