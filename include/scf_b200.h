@@ -46,7 +46,8 @@ extern "C" {
 #define SCFB_ERR_STATE (-6)    /* call sequence error (e.g. ERI not loaded yet)  */
 
 #define SCFB_LAYOUT_FULL 0    /* n^4 doubles, Julia order                                   */
-#define SCFB_LAYOUT_PACKED8 1 /* P(P+1)/2 doubles, P=n(n+1)/2, 8-fold-symmetric tensors only */
+#define SCFB_LAYOUT_PACKED8 1 /* ~P(P+1)/2 doubles, P=n(n+1)/2; ONLY for 8-fold-symmetric tensors AND
+                                 symmetric density / total_density arguments (every SCF satisfies both) */
 
 #define SCFB_ERI_HASH 0  /* dense splitmix64 family (DESIGN.md "synthetic inputs")  */
 #define SCFB_ERI_CHAIN 1 /* soft-Coulomb dimerised chain (physical, SCF converges) */
@@ -75,10 +76,12 @@ int scfb_eri_upload(scfb_handle_t h, const double* host_eri);
 int scfb_eri_upload_slabs(scfb_handle_t h, const double* host_slabs, int nu_first, int nu_count);
 /* Declare the shard complete after a sequence of partial scfb_eri_upload_slabs calls. */
 int scfb_eri_mark_ready(scfb_handle_t h);
-/* Fill the shard on the device from a closed-form synthetic family.  `aux` is family
- * specific: HASH ignores it; CHAIN expects 2*n doubles: x[n] then ... see DESIGN.md. */
+/* Fill the shard on the device from a closed-form synthetic family ("synthetic
+ * inputs").  `aux` is family specific: HASH ignores it (may be NULL); CHAIN expects
+ * 1 + n + n*n doubles: [soft, x[0..n), S[0..n*n) column-major] (site positions and overlap). */
 int scfb_eri_generate(scfb_handle_t h, int family, uint64_t seed, const double* aux);
-/* Copy the shard back (full layout only; debugging / parity at small n). */
+/* Copy the shard back exactly as stored (full: owned nu-slabs; packed8: the pre-scaled, padded
+ * packed rows — scfb_eri_bytes gives the size).  Debugging / parity at small n. */
 int scfb_eri_download(scfb_handle_t h, double* host_shard);
 
 /* ---- the hot path (JKBuilderFromTensor.jl:22-51) ----------------------------------- */
