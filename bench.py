@@ -138,6 +138,21 @@ class ClockSampler:
 
 
 # ---- the reference's CPU strategy on a bounded sample (oracle port) ------------------------
+def reference_strategy_slabs(eri, dens, total):
+    """J - K_s for the nu-slabs held in `eri` ((n,n,n,S), F-ordered), executed the way the
+    reference's two @tensor lines execute on a CPU: J = GEMV on the no-copy (ab)x(mu nu) matrix
+    view; every K line = permuted copy P[a,b,mu,nu] = eri[mu,b,a,nu] + GEMV."""
+    n, n_slabs = eri.shape[0], eri.shape[3]
+    n2 = n * n
+    m = eri.reshape(n2, n * n_slabs, order="F")
+    j = m.T @ total.reshape(n2, order="F")
+    out = []
+    for d in dens:                                                   # one permuted copy per K line
+        p = np.asfortranarray(eri.transpose(2, 1, 0, 3)).reshape(n2, n * n_slabs, order="F")
+        out.append((j - p.T @ d.reshape(n2, order="F")).reshape(n, n_slabs, order="F"))
+    return out
+
+
 def cpu_reference_sample(n, n_spin, n_slabs, steps):
     """J as a GEMV over the no-copy (ab)x(mu nu) view, K as permute-copy + GEMV per spin —
     how the reference's @tensor lines execute on the CPU — on `n_slabs`
@@ -153,12 +168,7 @@ def cpu_reference_sample(n, n_spin, n_slabs, steps):
     times = []
     for _ in range(steps + 1):
         t0 = time.perf_counter()
-        m = eri.reshape(n2, n * n_slabs, order="F")
-        j = m.T @ total.reshape(n2, order="F")
-        out = []
-        for d in dens:                                               # one permuted copy per K line
-            p = np.asfortranarray(eri.transpose(2, 1, 0, 3)).reshape(n2, n * n_slabs, order="F")
-            out.append(j - p.T @ d.reshape(n2, order="F"))
+        reference_strategy_slabs(eri, dens, total)
         times.append(time.perf_counter() - t0)
     t = float(np.median(times[1:]))                                   # first pass = warm-up
     try:
