@@ -19,14 +19,19 @@
 //   K'[i,k] += f D[j,l]   K'[i,l] += f D[j,k]   K'[j,k] += f D[i,l]   K'[j,l] += f D[i,k]
 // and K = K' + K'^T.  2 + 4 n_spin FMAs per 8 bytes: still HBM-bound (1.5-2.5 flop/B).
 //
-// Mapping: a warp owns (i, chunk of KC=8 consecutive k <= i, 64 consecutive l); each lane
-// owns an l-PAIR (one 128-bit load per k and row) and the warp loops over the rows j = 0..i,
-// each of which contributes one contiguous run of the packed row.  Sums whose output does not
-// depend on j (K'[i,k], K'[i,l], J~[q]) stay in registers for the whole item; per-row outputs
-// use a warp transpose-reduce (K'[j,k], J~[p]) or one RED per lane (K'[j,l]).  Warps are
-// fully independent (no CTA barrier); cross-warp combination is fp64 RED.ADD into zeroed
-// accumulators, so the packed path is deterministic only up to summation order (well inside
-// the 1e-12 relative gate).
+// Mapping (details at `packed_item`): one warp = one CTA owns (i, chunk of KC = 8 consecutive
+// k <= i, 64 consecutive l); each lane owns an l-PAIR (16 bytes per k and row) and the warp loops
+// over the rows j = 0..i, each of which contributes contiguous runs of the packed row.
+//   * all per-row data (ERI pairs from HBM, the density row from L2) travels through a 4-row
+//     cp.async (LDGSTS) ring in shared memory, three rows ahead of its use;
+//   * sums whose output does not depend on j (K'[i,k], K'[i,l], J~[q]) stay in registers for the
+//     whole item; K'[j,l] is lane-private (one RED per lane and row); the lane-reductions
+//     (K'[j,k], J~[p]) go through a conflict-free shared-memory tile flushed every few rows;
+//   * warps never synchronise with each other; cross-warp combination is fp64 RED.ADD into
+//     zeroed accumulators, so the packed path is deterministic only up to summation order
+//     (well inside the 1e-12 relative gate).
+// Compile-time knobs SCFB_EXP_NO_DLOAD / SCFB_EXP_NO_Z / SCFB_EXP_NO_FLUSH remove one cost
+// centre each (wrong results!) and exist only to reproduce the ablation in profiles/README.md.
 #include "scfb_internal.h"
 
 #include <cstdlib>
