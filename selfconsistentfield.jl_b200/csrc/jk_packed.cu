@@ -30,8 +30,8 @@
 //   * warps never synchronise with each other; cross-warp combination is fp64 RED.ADD into
 //     zeroed accumulators, so the packed path is deterministic only up to summation order
 //     (well inside the 1e-12 relative gate).
-// Compile-time knobs SCFB_EXP_NO_DLOAD / SCFB_EXP_NO_Z / SCFB_EXP_NO_FLUSH remove one cost
-// centre each (wrong results!) and exist only to reproduce the ablation in profiles/README.md.
+// Compile-time knobs SCFB_EXP_NO_Z / SCFB_EXP_NO_FLUSH remove one cost centre each (wrong
+// results!) and exist only to reproduce the ablation in profiles/README.md.
 #include "scfb_internal.h"
 
 #include <cstdlib>
