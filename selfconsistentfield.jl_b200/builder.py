@@ -57,6 +57,19 @@ class JKBuilderCUDA(TwoElectronBuilder):
         capi.check(capi.lib().scfb_eri_upload(self._h, capi.ptr(e)), self._h)
         return self
 
+    def upload_slabs(self, slabs, nu_first):
+        """Chunked upload (full layout): `slabs` is (n,n,n,count) holding the nu-slabs
+        nu_first..nu_first+count-1; slabs outside this builder's shard are skipped.  Call
+        `mark_ready()` once the shard is complete (load_integral_hdf5.jl:9-10 TODO: the reference
+        wants to avoid holding the whole tensor in host memory)."""
+        s = capi.as_f64_colmajor(slabs)
+        assert s.ndim == 4 and s.shape[:3] == (self.n_bas,) * 3
+        capi.check(capi.lib().scfb_eri_upload_slabs(self._h, capi.ptr(s), int(nu_first), s.shape[3]),
+                   self._h)
+
+    def mark_ready(self):
+        capi.check(capi.lib().scfb_eri_mark_ready(self._h), self._h)
+
     @classmethod
     def synthetic(cls, n_bas, family="hash", seed=20260101, aux=None, **kw):
         """ERI generated on the device from a closed-form family."""

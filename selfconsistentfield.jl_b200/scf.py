@@ -536,6 +536,10 @@ class DeviceScf:
         d = capi.as_f64_colmajor(density, (self.n, self.n, self.n_spin))
         self._call("scfb_scf_set_density", self.n_spin, capi.ptr(d))
 
+    def set_fock(self, fock):
+        f = capi.as_f64_colmajor(fock, (self.n, self.n, self.n_spin))
+        self._call("scfb_scf_set_fock", self.n_spin, capi.ptr(f))
+
     def fock(self):
         e = (C.c_double * 4)()
         norm = C.c_double()

@@ -274,3 +274,26 @@ def test_device_pointer_api_on_callers_stream(layout):
     stream_ms, total_ms = b.last_build_ms()
     assert 0 < stream_ms <= total_ms
     b.close()
+
+
+def test_chunked_slab_upload_equals_single_upload():
+    rng = np.random.default_rng(8)
+    n = 14
+    eri = np.asfortranarray(rng.standard_normal((n, n, n, n)))
+    dens = rng.standard_normal((n, n, 2))
+    total = rng.standard_normal((n, n))
+    whole = scf_b200.JKBuilderCUDA.from_tensor(eri)
+    jw, kw = whole.jk(dens, total)
+    whole.close()
+    for rank, n_ranks in ((0, 1), (1, 3)):
+        b = scf_b200.JKBuilderCUDA(n, rank=rank, n_ranks=n_ranks)
+        with pytest.raises(scf_b200.ScfbError):               # not ready yet
+            b.jk(dens, total)
+        for first in range(0, n, 4):                          # 4 slabs at a time, ragged tail
+            b.upload_slabs(eri[:, :, :, first:first + 4], first)
+        b.mark_ready()
+        j, k = b.jk(dens, total)
+        lo, hi = b.shard_range
+        assert np.array_equal(j[:, lo:hi], jw[:, lo:hi]) and np.array_equal(k[:, lo:hi], kw[:, lo:hi])
+        assert np.array_equal(b.eri_shard(), eri[:, :, :, lo:hi])
+        b.close()

@@ -255,3 +255,18 @@ def test_example_driver_config1(golden_dir, tmp_path):
         assert abs(float(line.split("=")[1]) - (-14.4868202421763)) < 1e-9 * 14.49
         z = np.load(out)
         assert abs(float(z["energy_coulomb"]) + float(z["energy_exchange"]) - float(z["energy_2e"])) < 1e-6
+
+
+def test_set_fock_then_roothaan_matches_oracle(golden_dir):
+    """scfb_scf_set_fock + scfb_scf_roothaan = compute_orbitals + compute_density on a given F."""
+    op, _ = oracle_problem(golden_dir, "integrals_be_3-21g", True)
+    cp, _ = cuda_problem(golden_dir, "integrals_be_3-21g", True)
+    f_ref, _, _ = o.compute_fock_matrix(op, o.compute_guess_hcore(op))
+    dev = S.DeviceScf(cp, cp.terms_2e["coulomb+exchange"])
+    dev.set_fock(f_ref)
+    dev.roothaan()
+    eps_ref, c_ref = o.compute_orbitals(op, f_ref)
+    assert np.abs(dev.get(dev.ORBEN)[:, 0] - eps_ref[:, 0]).max() < 1e-11
+    assert np.abs(dev.get(dev.DENSITY) - o.compute_density(op, c_ref)).max() < 1e-10
+    c = dev.get(dev.ORBCOEFF)[:, :, 0]
+    assert np.abs(c.T @ op.overlap @ c - np.eye(9)).max() < 1e-12
