@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """BASELINE.json config 2: synthetic (chain family) RHF, complete SCF loop with EDIIS->cDIIS,
 everything O(n^3)+ on the device.  Prints one JSON line with the per-phase wall time.
-  python benchmarks/scf_loop.py [--n-bas 128] [--layout full|packed8] [--check]"""
+  python benchmarks/scf_loop.py [--n-bas 128] [--layout full|packed8] [--unrestricted]
+(The energy is checked against the CPU oracle by tests/test_scf_gpu.py::test_config2_*, not here:
+only tests/, smoke() and bench.py's CPU baseline may touch oracle/.)"""
 import argparse
 import json
 import os
@@ -20,7 +22,6 @@ def main():
     p.add_argument("--n-bas", type=int, default=128)
     p.add_argument("--layout", default="full")
     p.add_argument("--unrestricted", action="store_true")
-    p.add_argument("--check", action="store_true", help="compare the energy with the CPU oracle")
     a = p.parse_args()
     n = a.n_bas
     model = scf_b200.synthetic.ChainModel(n)
@@ -57,18 +58,6 @@ def main():
             "ms_per_iteration": 1e3 * t_scf / res["n_iter"],
             "phase_ms_per_iteration": {k: 1e3 * v / res["n_iter"] for k, v in phases.items()},
             "eri_generate_seconds": t_gen, "fock_kernel_ms": builder.last_build_ms()[0]}
-    if a.check:
-        from oracle import scf_oracle as o
-        from oracle import synth
-        x, s, t, v, enn = synth.chain_matrices(n)
-        op = o.ScfProblem(s, model.n_elec(a.unrestricted), n, not a.unrestricted, {"nuclear_repulsion": enn},
-                          {"kinetic": t, "nuclear_attraction": v},
-                          {"coulomb+exchange": o.JKBuilderFromTensor(synth.chain_eri(n))})
-        t0 = time.perf_counter()
-        ref = o.run_scf(op, o.compute_guess_hcore(op), **kw)
-        line["oracle_seconds"] = time.perf_counter() - t0
-        line["oracle_e_total"] = ref["energies_newest"]["total"]
-        line["abs_energy_diff"] = abs(ref["energies_newest"]["total"] - line["e_total"])
     print(json.dumps(line))
 
 
