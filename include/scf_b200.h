@@ -17,7 +17,7 @@
  *   src/types/ScfProblem.jl:2-9                 abstract TwoElectronBuilder + add_2e_term!
  *   src/algorithms/JKBuilderFromTensor.jl:7-9   ERI storage           -> scfb_create / scfb_eri_*
  *   src/algorithms/JKBuilderFromTensor.jl:22-51 add_2e_term!          -> scfb_fock_jk
- *   src/parts/compute_fock_matrix.jl:8-71       Fock assembly/energies-> scfb_scf_fock
+ *   src/parts/compute_fock_matrix.jl:8-71       Fock assembly/energies-> scfb_fock_assemble, scfb_scf_fock
  *   src/parts/compute_pulay_error.jl:1-25       S D F - F D S         -> scfb_pulay_error, scfb_scf_fock
  *   src/parts/compute_orbitals.jl:4-19          eigen(F, S)           -> scfb_sygvd, scfb_scf_roothaan
  *   src/parts/compute_density.jl:4-35           C_occ C_occ'          -> scfb_scf_roothaan
@@ -146,6 +146,15 @@ int scfb_pulay_error(scfb_handle_t h, int n_spin, const double* fock, const doub
                      const double* overlap, double* error_out);
 int scfb_sygvd(scfb_handle_t h, int n_spin, int n_orb, const double* fock, const double* overlap,
                double* orben_out, double* orbcoeff_out);
+/* compute_density.jl:4-35: density_out[:,:,s] = C_occ,s C_occ,s' (alpha from block 0, beta from the
+ * last of the n_spin_c blocks of orbcoeff (n, n_orb, n_spin_c)); n_densities blocks are written. */
+int scfb_density(scfb_handle_t h, int n_spin_c, int n_densities, int n_occ_a, int n_occ_b, int n_orb,
+                 const double* orbcoeff, double* density_out);
+/* compute_fock_matrix.jl:38-58: fock_out = G + h_core, *e1e = tr(h_core Dtot),
+ * *e2e = tr(G_1 D_1) or (tr(G_1 D_1) + tr(G_2 D_2)) / 2. */
+int scfb_fock_assemble(scfb_handle_t h, int n_spin, const double* g, const double* h_core,
+                       const double* density, const double* total_density, double* fock_out,
+                       double* e1e, double* e2e);
 
 /* ---- multi-GPU exchange (one process per GPU) ------------------------- */
 /* Rank 0 calls scfb_comm_unique_id and ships the 128 bytes to the other ranks by any

@@ -65,6 +65,8 @@ _SIGNATURES = {
     "scfb_scf_get": [_h, C.c_int, _dp],
     "scfb_pulay_error": [_h, C.c_int, _dp, _dp, _dp, _dp],
     "scfb_sygvd": [_h, C.c_int, C.c_int, _dp, _dp, _dp, _dp],
+    "scfb_density": [_h, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp],
+    "scfb_fock_assemble": [_h, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp],
     "scfb_comm_unique_id": [C.c_char_p],
     "scfb_comm_init": [_h, C.c_char_p],
     "scfb_peer_export": [_h, C.c_char_p],

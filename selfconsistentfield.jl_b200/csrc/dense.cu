@@ -655,4 +655,84 @@ int scfb_sygvd(scfb_handle_t h, int n_spin, int n_orb, const double* fock, const
   return SCFB_OK;
 }
 
+// compute_density(problem, orbcoeff) (compute_density.jl:4-35): D_s = C_occ,s C_occ,s' with the
+// reference's block rule — alpha from spin block 0, beta from the LAST block of orbcoeff
+// (n_spin_c blocks of n x n_orb), n_densities blocks written.
+int scfb_density(scfb_handle_t h, int n_spin_c, int n_densities, int n_occ_a, int n_occ_b, int n_orb,
+                 const double* orbcoeff, double* density_out) {
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  const int n = h->n;
+  SCFB_REQUIRE(h, (n_spin_c == 1 || n_spin_c == 2) && (n_densities == 1 || n_densities == 2) &&
+                      orbcoeff && density_out && n_orb >= 1 && n_orb <= n, "bad arguments");
+  // compute_density.jl:8-10
+  SCFB_REQUIRE(h, n_occ_a >= 0 && n_occ_b >= 0 && n_occ_a < n_orb && n_occ_b < n_orb,
+               "n_elec of alpha and beta should be less than n_orb");
+  SCFB_CUDA(h, cudaSetDevice(h->device));
+  if (int rc = ensure_dense_handles(h)) return rc;
+  const size_t cn = (size_t)n * n_orb, n2 = (size_t)n * n;
+  double* buf = nullptr;
+  SCFB_CUDA(h, cudaMalloc(&buf, (n_spin_c * cn + n_densities * n2) * sizeof(double)));
+  double* C = buf;
+  double* D = buf + n_spin_c * cn;
+  cudaMemcpyAsync(C, orbcoeff, n_spin_c * cn * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  int rc = SCFB_OK;
+  const int nocc[2] = {n_occ_a, n_occ_b};
+  for (int s = 0; s < n_densities && rc == SCFB_OK; ++s) {
+    const double* Cs = C + (s == 0 ? 0 : (size_t)(n_spin_c - 1) * cn);
+    if (nocc[s] == 0) {
+      cudaMemsetAsync(D + s * n2, 0, n2 * sizeof(double), h->stream);
+      continue;
+    }
+    const double one = 1.0, zero = 0.0;
+    if (cublasDgemm(static_cast<cublasHandle_t>(h->blas), CUBLAS_OP_N, CUBLAS_OP_T, n, n, nocc[s], &one,
+                    Cs, n, Cs, n, &zero, D + s * n2, n) != CUBLAS_STATUS_SUCCESS)
+      rc = scfb_fail(h, SCFB_ERR_CUSOLVER, "cublasDgemm failed in scfb_density");
+    h->launches += 1;
+  }
+  cudaMemcpyAsync(density_out, D, n_densities * n2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(buf);
+  if (rc) return rc;
+  if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "density: %s", cudaGetErrorString(e));
+  return SCFB_OK;
+}
+
+// The assembly half of compute_fock_matrix (compute_fock_matrix.jl:38-58) on host arrays:
+// e1e = tr(h_core Dtot), e2e = tr(G_1 D_1) (one block) or (tr(G_1 D_1) + tr(G_2 D_2))/2,
+// fock_out[:,:,s] = G[:,:,s] + h_core.
+int scfb_fock_assemble(scfb_handle_t h, int n_spin, const double* g, const double* h_core,
+                       const double* density, const double* total_density, double* fock_out,
+                       double* e1e, double* e2e) {
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  SCFB_REQUIRE(h, (n_spin == 1 || n_spin == 2) && g && h_core && density && total_density && fock_out,
+               "bad arguments");
+  SCFB_CUDA(h, cudaSetDevice(h->device));
+  const int n = h->n;
+  const size_t n2 = (size_t)n * n, ns = n_spin;
+  double* buf = nullptr;
+  SCFB_CUDA(h, cudaMalloc(&buf, (3 * ns * n2 + 2 * n2 + 8) * sizeof(double)));
+  double *G = buf, *D = G + ns * n2, *F = D + ns * n2, *H = F + ns * n2, *T = H + n2, *scal = T + n2;
+  cudaMemcpyAsync(G, g, ns * n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(D, density, ns * n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(H, h_core, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(T, total_density, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  fock_add_kernel<<<blocks_for(n2 * ns), 256, 0, h->stream>>>(G, H, F, n2, n_spin);
+  TraceBatch tb{};
+  tb.p[0] = {H, T, 1};
+  tb.p[1] = {G, D, 1};
+  tb.p[2] = {G + (ns - 1) * n2, D + (ns - 1) * n2, 1};
+  trace_kernel<<<3, 1024, 0, h->stream>>>(tb, n, scal);
+  h->launches += 2;
+  double v[3] = {0, 0, 0};
+  cudaMemcpyAsync(fock_out, F, ns * n2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaMemcpyAsync(v, scal, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(buf);
+  if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "fock_assemble: %s", cudaGetErrorString(e));
+  if (e1e) *e1e = v[0];
+  if (e2e) *e2e = n_spin == 1 ? v[1] : 0.5 * (v[1] + v[2]);
+  return SCFB_OK;
+}
+
 }  // extern "C"

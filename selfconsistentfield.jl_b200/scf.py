@@ -191,16 +191,16 @@ def compute_fock_matrix(problem, density, **kwargs):
     g = np.zeros((n_bas, n_bas, n_spin), order="F")
     for _label, builder in problem.terms_2e.items():
         builder.add_2e_term(g, density, total_density)        # the plugin boundary
-    energies = {"0e": sum(problem.terms_0e.values()),
-                "1e": float(np.sum(h_core * total_density.T))}
-    if n_spin == 1:
-        energies["2e"] = float(np.sum(g[:, :, 0] * density[:, :, 0].T))
-    else:
-        energies["2e"] = 0.5 * float(np.sum(g[:, :, 0] * density[:, :, 0].T)
-                                     + np.sum(g[:, :, 1] * density[:, :, 1].T))
-    energies["total"] = energies["0e"] + energies["1e"] + energies["2e"]
-    fock = g + h_core[:, :, None]
     dev = _any_cuda_builder(problem)
+    fock = np.empty((n_bas, n_bas, n_spin), order="F")
+    e1e, e2e = C.c_double(), C.c_double()
+    gd, hd = capi.as_f64_colmajor(g), capi.as_f64_colmajor(h_core)
+    dd, td = capi.as_f64_colmajor(density), capi.as_f64_colmajor(total_density)
+    capi.check(capi.lib().scfb_fock_assemble(dev._h, n_spin, capi.ptr(gd), capi.ptr(hd), capi.ptr(dd),
+                                             capi.ptr(td), capi.ptr(fock), C.byref(e1e), C.byref(e2e)),
+               dev._h)
+    energies = {"0e": sum(problem.terms_0e.values()), "1e": e1e.value, "2e": e2e.value}
+    energies["total"] = energies["0e"] + energies["1e"] + energies["2e"]
     if n_spin == 2 and problem.restricted:
         fock2 = compute_roothaan_effective_fock(fock, density, overlap)
         error_pulay = compute_pulay_error(fock2, total_density, overlap, builder=dev)
@@ -230,13 +230,14 @@ def compute_density(problem, orbcoeff):
     n_bas, n_orb, n_spin = orbcoeff.shape
     assert n_spin == 1 or n_spin == 2, "Only one or two spin components allowed"
     assert n_elec[0] < n_orb and n_elec[1] < n_orb, "n_elec of alpha and beta should be less than n_orb"
-    cocc = (orbcoeff[:, :n_elec[0], 0], orbcoeff[:, :n_elec[1], n_spin - 1])
     n_densities = n_spin
     if (not problem.restricted) or n_elec[0] != n_elec[1]:
         n_densities = 2
     density = np.empty((n_bas, n_bas, n_densities), order="F")
-    for s in range(n_densities):
-        density[:, :, s] = cocc[s] @ cocc[s].T
+    dev = _any_cuda_builder(problem)
+    c = capi.as_f64_colmajor(orbcoeff)
+    capi.check(capi.lib().scfb_density(dev._h, n_spin, n_densities, n_elec[0], n_elec[1], n_orb,
+                                       capi.ptr(c), capi.ptr(density)), dev._h)
     return density
 
 
