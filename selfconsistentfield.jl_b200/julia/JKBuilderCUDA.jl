@@ -22,8 +22,8 @@ module SCFB200
 using SelfConsistentField
 import SelfConsistentField: TwoElectronBuilder, add_2e_term!
 
-export JKBuilderCUDA, with_cuda_builder, jk_split, scf_device_setup!, scf_device_fock!,
-       scf_device_roothaan!, scf_device_diis_push!, scf_device_diis_extrapolate!
+export JKBuilderCUDA, with_cuda_builder, jk_split, run_scf_device, scf_device_setup!,
+       scf_device_fock!, scf_device_roothaan!, scf_device_diis_push!, scf_device_diis_extrapolate!
 
 const libscf = get(ENV, "SCFB200_LIB", joinpath(@__DIR__, "..", "libscf_b200.so"))
 
@@ -198,6 +198,92 @@ function scf_device_get(b::JKBuilderCUDA, what::Integer, n_spin::Integer)
     check(ccall((:scfb_scf_get, libscf), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}),
                 b.handle, what, out), b.handle)
     out
+end
+
+# ---------------------------------------------------------------------------------------
+# run_scf with the whole iteration on the device.  Control flow, defaults and the result Dict
+# follow src/run_scf.jl:4-65 line by line; the small coefficient solves are the reference's
+# own `diis_solve_coefficients` methods (cDIIS.jl:33-63, EDIIS.jl:20-44), fed with matrices
+# assembled from the rows the device returns.  (Python twin, which is what is tested:
+# selfconsistentfield.jl_b200/scf.py `_run_scf_device`.)
+# ---------------------------------------------------------------------------------------
+using DataStructures: CircularBuffer
+import SelfConsistentField: cDIIS, EDIIS, diis_solve_coefficients, check_convergence,
+                            ScfConvergence
+
+"Insert the new first row/column of a DIIS matrix (newest first) and drop the oldest beyond `cap`."
+function push_row(B::Matrix{Float64}, row::Vector{Float64}, cap::Int)
+    m = length(row)
+    Bn = zeros(m, m)
+    Bn[1, :] = row; Bn[:, 1] = row
+    k = m - 1
+    k > 0 && (Bn[2:end, 2:end] = B[1:k, 1:k])
+    Bn
+end
+
+function run_scf_device(problem::ScfProblem, guess_density::AbstractArray;
+                        max_iter=100, ediis_max_error_norm=0.1, n_diis_size=5,
+                        conditioning_threshold=1e-14, coefficient_threshold=1e-6, kwargs...)
+    @assert length(problem.terms_2e) == 1
+    b = first(values(problem.terms_2e))::JKBuilderCUDA
+    n_spin = size(guess_density, 3)
+    scf_device_setup!(b, problem; n_diis_size=n_diis_size)
+    scf_device_set_density!(b, guess_density)
+    energies, _ = scf_device_fock!(b)                       # run_scf.jl:16
+    use_ediis = true                                        # run_scf.jl:8
+    B = [zeros(0, 0) for _ in 1:n_spin]
+    energybuffer = CircularBuffer{Dict}(n_diis_size)
+    scfconv = nothing; n_iter = 0; newenergies = energies
+    for i in 1:max_iter
+        n_iter = i
+        # --- compute_next_iterate (parts/diis.jl:4-36) ---
+        pushfirst!(energybuffer, energies)
+        for σ in 1:n_spin
+            rc, re = scf_device_diis_push!(b, σ)
+            B[σ] = push_row(B[σ], use_ediis ? re : rc, n_diis_size)
+        end
+        acc = use_ediis ? EDIIS(problem; n_diis_size=n_diis_size) : cDIIS(problem; n_diis_size=n_diis_size)
+        system(σ) = use_ediis ? B[σ] : [B[σ] ones(size(B[σ], 1)); ones(size(B[σ], 1))' 0.0]
+        # sync_spins = true: EDIIS adds the spin blocks (EDIIS.jl:126-128), cDIIS keeps the
+        # alpha block (cDIIS.jl:69-72)
+        A = (n_spin == 2 && use_ediis) ? system(1) + system(2) : system(1)
+        c, n_purge = diis_solve_coefficients(acc, A; conditioning_threshold=conditioning_threshold,
+                                             energybuffer=energybuffer)
+        for σ in 1:n_spin
+            mask = map(x -> abs(x) >= coefficient_threshold, c); mask[1] = true   # diis.jl:45-47
+            c[argmax(c)] += sum(c[.!mask])
+            scf_device_diis_extrapolate!(b, σ, Vector{Float64}(c .* mask))
+        end
+        for σ in 1:n_spin
+            scf_device_diis_purge!(b, σ, n_purge)
+            n_purge > 0 && (m = max(0, size(B[σ], 1) - (n_purge + 1)); B[σ] = B[σ][1:m, 1:m])
+        end
+        # --- roothan_step (Roothaan.jl:5-7) ---
+        scf_device_roothaan!(b)
+        newenergies, error_norm = scf_device_fock!(b)
+        # --- check_convergence (check_convergence.jl:13-37), signed changes ---
+        change = Dict(k => newenergies[k] - v for (k, v) in energies)
+        converged = !(error_norm >= get(kwargs, :max_error_norm, 5e-7) ||
+                      change["total"] >= get(kwargs, :max_energy_total_change, 1.25e-7) ||
+                      change["1e"] >= get(kwargs, :max_energy_1e_change, 5e-5))
+        scfconv = ScfConvergence(error_norm, change, converged)
+        converged && break
+        if error_norm < ediis_max_error_norm && use_ediis      # run_scf.jl:42-46
+            use_ediis = false
+            scf_device_diis_reset!(b)
+            B = [zeros(0, 0) for _ in 1:n_spin]
+        end
+        energies = newenergies
+    end
+    stale = scfconv.is_converged          # run_scf.jl:40 breaks before :48
+    Dict("n_iter" => n_iter, "n_applies" => NaN, "problem" => problem,
+         "orben" => scf_device_get(b, stale ? 7 : 5, n_spin)[1:problem.n_orb, :],
+         "orbcoeff" => scf_device_get(b, stale ? 6 : 4, n_spin)[:, 1:problem.n_orb, :],
+         "density" => scf_device_get(b, stale ? 8 : 2, n_spin),
+         "converged" => scfconv.is_converged,
+         "fock" => scf_device_get(b, stale ? 0 : 1, n_spin),
+         "energies" => stale ? energies : newenergies,
+         "error_norm" => scfconv.error_norm, "energy_change" => scfconv.energy_change)
 end
 
 end # module
