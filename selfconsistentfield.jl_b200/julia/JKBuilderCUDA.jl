@@ -22,7 +22,7 @@ module SCFB200
 using SelfConsistentField
 import SelfConsistentField: TwoElectronBuilder, add_2e_term!
 
-export JKBuilderCUDA, with_cuda_builder, jk_split, run_scf_device, scf_device_setup!,
+export JKBuilderCUDA, with_cuda_builder, upload_slabs!, mark_ready!, jk_split, run_scf_device, scf_device_setup!,
        scf_device_fock!, scf_device_roothaan!, scf_device_diis_push!, scf_device_diis_extrapolate!
 
 const libscf = get(ENV, "SCFB200_LIB", joinpath(@__DIR__, "..", "libscf_b200.so"))
@@ -64,6 +64,23 @@ mutable struct JKBuilderCUDA <: TwoElectronBuilder
         obj
     end
 end
+
+"""
+Chunked upload for tensors too large for host memory (load_integral_hdf5.jl:9-10 TODO):
+`slabs[:,:,:,1:count]` are the nu-slabs `nu_first .. nu_first+count-1` (1-based like every Julia
+index; e.g. `h5f["electron_repulsion_bbbb"][:,:,:,r]` for a range `r`).  Slabs outside this
+builder's shard are skipped; call `mark_ready!` once the shard is complete.
+"""
+function upload_slabs!(b::JKBuilderCUDA, slabs::AbstractArray{Float64,4}, nu_first::Integer)
+    @assert size(slabs)[1:3] == (b.n_bas, b.n_bas, b.n_bas)
+    dense = Array{Float64,4}(slabs)
+    check(ccall((:scfb_eri_upload_slabs, libscf), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint),
+                b.handle, dense, nu_first - 1, size(dense, 4)), b.handle)
+    b
+end
+
+mark_ready!(b::JKBuilderCUDA) =
+    (check(ccall((:scfb_eri_mark_ready, libscf), Cint, (Ptr{Cvoid},), b.handle), b.handle); b)
 
 "Equivalent of `JKBuilderFromTensor(eri)`: upload the dense (n,n,n,n) tensor once."
 function JKBuilderCUDA(eri::AbstractArray{Float64,4}; kwargs...)

@@ -176,6 +176,48 @@ class MiniH5:
         arr = arr.reshape(dims).copy()
         return arr
 
+    def shape(self, path):
+        """Dataset dimensions (C order, as stored) without reading the data."""
+        for mtype, _, p in self._messages(self._lookup(path)["ohdr"] + self.base):
+            if mtype == 0x0001:
+                ver, rank, _flags = struct.unpack_from("<BBB", p, 0)
+                return tuple(struct.unpack_from(f"<{rank}Q", p, 8 if ver == 1 else 4)) if rank else ()
+        raise H5FormatError(f"{path}: not a dataset")
+
+    def read_rows(self, path, lo, hi):
+        """Rows [lo, hi) of the FIRST (slowest) file dimension of a chunked or contiguous dataset;
+        only the chunks that intersect the range are inflated, so a huge ERI can be streamed to
+        the device slab by slab (the reference's own TODO, load_integral_hdf5.jl:9-10).
+        For `electron_repulsion_bbbb` file row v is exactly Julia's column-major slab eri[:,:,:,v]."""
+        ent = self._lookup(path)
+        dims = dtype = layout = None
+        filters = []
+        for mtype, _, p in self._messages(ent["ohdr"] + self.base):
+            if mtype == 0x0001:
+                ver, rank, _flags = struct.unpack_from("<BBB", p, 0)
+                dims = struct.unpack_from(f"<{rank}Q", p, 8 if ver == 1 else 4)
+            elif mtype == 0x0003:
+                dtype = self._datatype(p)
+            elif mtype == 0x0008:
+                layout = self._layout(p)
+            elif mtype == 0x000B:
+                filters = self._filters(p)
+        if dims is None or dtype is None or layout is None or not dims:
+            raise H5FormatError(f"{path}: not an array dataset")
+        if not (0 <= lo <= hi <= dims[0]):
+            raise ValueError(f"row range [{lo}, {hi}) outside [0, {dims[0]})")
+        kind, np_dtype, esize = dtype
+        if kind == "vlen_str":
+            raise H5FormatError("row reads of strings unsupported")
+        sub = (hi - lo,) + tuple(dims[1:])
+        if layout[0] == "contiguous":
+            row = int(np.prod(dims[1:])) * esize
+            start = layout[1] + self.base + lo * row
+            return np.frombuffer(self.buf[start:start + (hi - lo) * row], dtype=np_dtype).reshape(sub).copy()
+        if layout[0] != "chunked":
+            raise H5FormatError(f"layout {layout[0]} unsupported")
+        return self._read_chunked(layout, dims, np_dtype, esize, filters, first_dim_range=(lo, hi))
+
     def _datatype(self, p):
         cls = p[0] & 0x0F
         bits0 = p[1]
@@ -222,10 +264,11 @@ class MiniH5:
             out.append(fid)
         return out
 
-    def _read_chunked(self, layout, dims, np_dtype, esize, filters):
+    def _read_chunked(self, layout, dims, np_dtype, esize, filters, first_dim_range=None):
         _, btree, cdims, _el = layout
         rank = len(dims)
-        out = np.zeros(dims, dtype=np_dtype)
+        lo, hi = first_dim_range if first_dim_range is not None else (0, dims[0])
+        out = np.zeros((hi - lo,) + tuple(dims[1:]), dtype=np_dtype)
         b = self.buf
         chunk_count = int(np.prod(cdims))
 
@@ -245,6 +288,8 @@ class MiniH5:
                 if level > 0:
                     walk(child)
                     continue
+                if offs[0] >= hi or offs[0] + cdims[0] <= lo:
+                    continue          # chunk entirely outside the requested rows
                 raw = b[child: child + csize]
                 for fid in reversed(filters):
                     if fid == 1:
@@ -255,9 +300,12 @@ class MiniH5:
                     else:
                         raise H5FormatError(f"filter {fid} unsupported")
                 chunk = np.frombuffer(raw, dtype=np_dtype, count=chunk_count).reshape(cdims)
-                # edge chunks are stored full-size: crop
-                sl_out = tuple(slice(o, min(o + c, d)) for o, c, d in zip(offs, cdims, dims))
-                sl_in = tuple(slice(0, s.stop - s.start) for s in sl_out)
+                # edge chunks are stored full-size: crop (and clip to the requested rows)
+                r0, r1 = max(offs[0], lo), min(offs[0] + cdims[0], dims[0], hi)
+                sl_out = (slice(r0 - lo, r1 - lo),) + tuple(
+                    slice(o, min(o + c, d)) for o, c, d in zip(offs[1:], cdims[1:], dims[1:]))
+                sl_in = (slice(r0 - offs[0], r1 - offs[0]),) + tuple(
+                    slice(0, s_.stop - s_.start) for s_ in sl_out[1:])
                 out[sl_out] = chunk[sl_in]
 
         walk(btree + self.base)

@@ -104,12 +104,33 @@ def assemble_hf_problem(system, integrals, n_orb=None, restricted=None, **kwargs
                       bool(restricted), terms_0e, terms_1e, terms_2e)
 
 
-def load_integral_hdf5(path, **builder_kw):
+def load_integral_hdf5(path, slab_batch=None, **builder_kw):
     """load_integral_hdf5.jl:6-55 with the ERI going straight into a JKBuilderCUDA.  The file
     is parsed by the package's own minimal HDF5 reader (no libhdf5 here); dims are reversed
-    like HDF5.jl does (Julia eri[i,j,k,l] == file[l,k,j,i])."""
+    like HDF5.jl does (Julia eri[i,j,k,l] == file[l,k,j,i]).
+
+    slab_batch=N streams the tensor to the device N nu-slabs at a time (file row v IS Julia's
+    column-major slab eri[:,:,:,v]), reading only the rows this builder's shard owns — the
+    whole tensor never exists on the host (the reference's TODO at load_integral_hdf5.jl:9-10);
+    `integrals["electron_repulsion_bbbb"]` is then None."""
     from .minih5 import MiniH5
     f = MiniH5(path)
+    if slab_batch:
+        n = f.shape("electron_repulsion_bbbb")[0]
+        builder = JKBuilderCUDA(n, **builder_kw)
+        assert builder.layout == "full", "slab streaming targets the full layout"
+        lo, hi = builder.shard_range
+        for first in range(lo, hi, slab_batch):
+            rows = f.read_rows("electron_repulsion_bbbb", first, min(first + slab_batch, hi))
+            builder.upload_slabs(rows.T, first)           # (S,n,n,n) C-order == (n,n,n,S) F-order
+        builder.mark_ready()
+        small = {k: f.read(k) for k in ("kinetic_bb", "nuclear_attraction_bb", "overlap_bb")}
+        system, integrals = _integrals_from_arrays(
+            dict(small, electron_repulsion_bbbb=None), f.read("system/nelec"),
+            f.read("system/atom_numbers"), f.read("system/coords"), f.read("discretisation/basis_type"),
+            f.read("discretisation/basis_set_name") if "basis_set_name" in f.keys("discretisation") else None,
+            builder_kw, builder=builder)
+        return system, integrals
     return _integrals_from_arrays(
         {k: f.read(k) for k in ("electron_repulsion_bbbb", "kinetic_bb", "nuclear_attraction_bb",
                                 "overlap_bb")},
@@ -126,8 +147,9 @@ def load_integral_npz(path, **builder_kw):
                                   str(z["basis_set_name"]), builder_kw)
 
 
-def _integrals_from_arrays(a, nelec, atnums, coords, basis_type, basis_set_name, builder_kw):
-    eri = np.asarray(a["electron_repulsion_bbbb"]).T     # dims reversed, same bytes
+def _integrals_from_arrays(a, nelec, atnums, coords, basis_type, basis_set_name, builder_kw,
+                           builder=None):
+    eri = None if builder is not None else np.asarray(a["electron_repulsion_bbbb"]).T  # dims reversed
     system = {"coords": np.asarray(coords, dtype=float), "atom_numbers": np.asarray(atnums),
               "n_elec": (int(nelec[0]), int(nelec[1]))}
     integrals = {
@@ -135,7 +157,7 @@ def _integrals_from_arrays(a, nelec, atnums, coords, basis_type, basis_set_name,
         "nuclear_attraction_bb": np.asarray(a["nuclear_attraction_bb"]).T.copy(),
         "overlap_bb": np.asarray(a["overlap_bb"]).T.copy(),
         "electron_repulsion_bbbb": eri,
-        "jk_builder_bb": JKBuilderCUDA.from_tensor(eri, **builder_kw),
+        "jk_builder_bb": builder if builder is not None else JKBuilderCUDA.from_tensor(eri, **builder_kw),
         "discretisation": {"basis_type": basis_type, "basis_set_name": basis_set_name},
     }
     return system, integrals

@@ -136,3 +136,17 @@ def test_minih5_rejects_garbage(tmp_path):
     p.write_bytes(b"not an hdf5 file at all")
     with pytest.raises(H5FormatError):
         MiniH5(str(p))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DATA), reason="reference checkout not present")
+def test_minih5_row_ranges_equal_the_full_read():
+    """Slab streaming: rows [lo, hi) of the chunked ERI dataset (chunks of 5 along that axis)."""
+    from scf_b200.minih5 import MiniH5
+    h = MiniH5(os.path.join(REF_DATA, "integrals_c_3-21g.hdf5"))
+    assert h.shape("electron_repulsion_bbbb") == (9, 9, 9, 9) and h.shape("system/nelec") == (2,)
+    full = h.read("electron_repulsion_bbbb")
+    for lo, hi in ((0, 9), (0, 1), (3, 7), (4, 6), (8, 9), (5, 5)):
+        assert np.array_equal(h.read_rows("electron_repulsion_bbbb", lo, hi), full[lo:hi])
+    assert np.array_equal(h.read_rows("system/coords", 0, 1), h.read("system/coords"))
+    with pytest.raises(ValueError):
+        h.read_rows("electron_repulsion_bbbb", 3, 12)
