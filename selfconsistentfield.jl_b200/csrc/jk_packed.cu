@@ -105,12 +105,6 @@ __device__ __forceinline__ bool transpose_reduce_owner(int lane) {
   return V == 8 ? (lane & 3) == 0 : (lane & 7) == 0;
 }
 
-__device__ __forceinline__ double warp_sum(double x) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  return x;
-}
-
 // One work item of one warp.  D: (n*n + DPAD) x NSPIN symmetric, padded so that the KC-wide
 // uniform reads D[j, k0..k0+KC) and the pair reads D[j, l0..l0+1] never leave the allocation;
 // dq2: 2*Dtot in pair space, stored with the SAME padded segment offsets seg_off(k)+l (pads
@@ -435,19 +429,7 @@ jk_packed_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Bt
     packed_item<NSPIN, KC, 1, VECD>(eri_i, D, dstride, dq2, Kp, Jp, ys, ring, ring_dl, ring_dk, n, i, k0, l0, lane, rot);
 }
 
-// ------------------------------------------------------------------------------------------
-// v3: the same item decomposition, but the ERI stream is decoupled from the math with the
-// Blackwell/Hopper async-copy machinery: one producer warp issues 1-D bulk copies
-// (cp.async.bulk -> SASS UBLKCP, the TMA engine) of each row's k-segments into a ring of
-// shared-memory stages guarded by mbarriers; four consumer warps pull their l-pairs out of
-// the ring with immediate-offset LDS.128.  The padded layout makes every copy 16-byte aligned
-// and a multiple of 16 bytes.  Consumers never wait on DRAM latency and carry no prefetch
-// registers; the producer keeps STAGES rows (STAGES * KC * 2 KB) in flight per CTA.
-// ------------------------------------------------------------------------------------------
-constexpr int CW = 4;            // consumer warps per CTA
-constexpr int LW = 2 * 32 * CW;  // l values per CTA = 256
-constexpr int STAGES = 4;
-
+// ---- mbarrier / bulk-copy (TMA) helpers ----------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -457,9 +439,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -481,102 +460,61 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       : "memory");
 }
 
-// grid = (n_kchunks, n_i_owned, n_lblocks of LW); block = (CW + 1) warps.
-template <int NSPIN, int KC, int MINB>
-__global__ void __launch_bounds__(32 * (CW + 1), MINB)
-jk_packed_tma_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Btab,
-                     uint64_t shard_offset, const double* __restrict__ D,
-                     const double* __restrict__ dq2, double* __restrict__ Kp,
-                     double* __restrict__ Jp, int n, int i_lo) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* ring = reinterpret_cast<double*>(smem_raw);                       // [STAGES][KC][LW]
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + STAGES * KC * LW);    // [STAGES]
-  uint64_t* empty = full + STAGES;                                          // [STAGES]
+// ------------------------------------------------------------------------------------------
+// v4 (SCFB_PACKED_TMA=1, measured slower: profiles/README.md): the one-warp work item of `packed_item`, with every per-row operand delivered by the TMA
+// engine instead of per-lane LDGSTS.  ncu on v2 shows the LSU data pipe at 66 % with two warps per
+// scheduler: each row costs ~160 LSU cycles per warp, 80 of them the LDGSTS writes of the ERI pairs
+// and of the density row.  Here lane 0 posts, three rows ahead, one 1-D bulk copy (cp.async.bulk ->
+// SASS UBLKCP) per k-segment (<= 512 B: this warp's 64 l values), one per spin for D[j, wl..wl+63]
+// and one per spin for D[j, k0..k0+KC), all completing on the stage's mbarrier; the warp that
+// issued them is also their only consumer, so there is no "empty" barrier, no second warp and no
+// CTA-level synchronisation.  2 Dtot[(i,j)] (8 bytes, not bulk-copyable) is an ordinary load issued
+// one row early.  Requires n even (16-byte alignment of the density rows).
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int bulk_stage_doubles(int nspin, int kc) {
+  return kc * 64 + nspin * 64 + nspin * kc;
+}
+__host__ __device__ constexpr size_t bulk_smem_bytes(int nspin, int kc) {
+  return (size_t)packed_rb(nspin, kc) * (nspin * kc + 1) * YS * sizeof(double)
+         + (size_t)DEPTH * bulk_stage_doubles(nspin, kc) * sizeof(double) + DEPTH * sizeof(uint64_t);
+}
 
-  const int i = i_lo + blockIdx.y;
-  const int k0 = blockIdx.x * KC;
-  if (k0 > i) return;
-  const int lb = blockIdx.z * LW;  // first l of this CTA
+template <int NSPIN, int KC, int MODE>
+__device__ __forceinline__ void packed_item_bulk(const double* __restrict__ eri_i,
+                                                 const double* __restrict__ D, size_t dstride,
+                                                 const double* __restrict__ dq2,
+                                                 double* __restrict__ Kp, double* __restrict__ Jp,
+                                                 double* __restrict__ ys, double* __restrict__ stages,
+                                                 uint64_t* __restrict__ bars, int n, int i, int k0,
+                                                 int wl, int lane, uint32_t rot) {
+  constexpr int NV = NSPIN * KC + 1;
+  constexpr int RB = packed_rb(NSPIN, KC);
+  constexpr int STG = bulk_stage_doubles(NSPIN, KC);
+  const int l0 = wl + 2 * lane;
   const int kmax = min(k0 + KC - 1, i);
-  if (lb > kmax) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // consumer warps whose 64 l values start beyond kmax have nothing to do
-  const int live = min(CW, (kmax - lb) / 64 + 1);
-  const bool diag = kmax == i;
-  const int rows = i + 1;
-  const uint64_t Ei = seg_off(i);
-  const double* eri_i = eri + (Btab[i] - shard_offset);
-  const uint32_t rot = blockIdx.x * 40503u + blockIdx.z * 9973u + blockIdx.y * 17u;
-  const int j_first = (int)(rot % (uint32_t)rows);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full + s, 1);
-      mbar_init(empty + s, live);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp == CW) {
-    // ===== producer: one lane feeds the ring =====
-    if (lane != 0) return;
-    int j = j_first;
-    const double* row = eri_i + (uint64_t)j * Ei + seg_off(j);
-    for (int step = 0; step < rows; ++step) {
-      const int s = step % STAGES;
-      mbar_wait(empty + s, ((step / STAGES) & 1) ^ 1);
-      uint32_t len[KC], total = 0;
-#pragma unroll
-      for (int t = 0; t < KC; ++t) {
-        const int k = k0 + t;
-        // stored (padded) length of segment k in row (i,j), clipped to this CTA's l window
-        int seg = k > i ? 0 : ((k < i ? k : j) + 2) & ~1;
-        seg = seg - lb;
-        len[t] = seg <= 0 ? 0u : (uint32_t)(seg < LW ? seg : LW);
-        total += len[t];
-      }
-      mbar_expect_tx(full + s, total * 8u);
-      double* dst = ring + (size_t)s * KC * LW;
-#pragma unroll
-      for (int t = 0; t < KC; ++t)
-        if (len[t]) bulk_g2s(dst + t * LW, row + seg_off(min(k0 + t, i)) + lb, len[t] * 8u, full + s);
-      const int jn = j + 1 == rows ? 0 : j + 1;
-      row = jn ? row + Ei + ((j + 2) & ~1) : eri_i;
-      j = jn;
-    }
-    return;
-  }
-  if (warp >= live) return;
-
-  // ===== consumers =====
-  const size_t n2 = (size_t)n * n;
-  const int m = warp * 32 + lane;          // l-pair within the CTA window
-  const int l0 = lb + 2 * m;
-  const bool l0_in = l0 <= kmax, l1_in = l0 + 1 <= kmax;
+  const bool l0_in = MODE == 0 || l0 <= kmax, l1_in = MODE == 0 || l0 + 1 <= kmax;
   const int lc = l0_in ? l0 : 0;
+  const uint64_t Ei = seg_off(i);
 
   double di_l[NSPIN][2], di_k[NSPIN][KC], dq[KC][2];
   bool ok[KC];
-  uint32_t joff[KC];
 #pragma unroll
   for (int s = 0; s < NSPIN; ++s) {
-    const double* di = D + s * n2 + (size_t)i * n;
+    const double* di = D + s * dstride + (size_t)i * n;
     di_l[s][0] = __ldg(di + lc);
-    di_l[s][1] = l1_in ? __ldg(di + lc + 1) : 0.0;
+    di_l[s][1] = __ldg(di + lc + 1);
   }
 #pragma unroll
   for (int t = 0; t < KC; ++t) {
     const int k = k0 + t;
-    ok[t] = k <= i && l0 <= k;
+    ok[t] = MODE == 0 || (k <= i && l0 <= k);
     const int kc = k <= i ? k : i;
-    joff[t] = (uint32_t)seg_off(kc) + (uint32_t)lc;
-    const double2 q2 =
-        ok[t] ? __ldg(reinterpret_cast<const double2*>(dq2 + joff[t])) : make_double2(0.0, 0.0);
+    const double2 q2 = ok[t] ? __ldg(reinterpret_cast<const double2*>(dq2 + seg_off(kc) + lc))
+                             : make_double2(0.0, 0.0);
     dq[t][0] = q2.x;
     dq[t][1] = q2.y;
 #pragma unroll
-    for (int s = 0; s < NSPIN; ++s) di_k[s][t] = __ldg(D + s * n2 + (size_t)i * n + kc);
+    for (int s = 0; s < NSPIN; ++s) di_k[s][t] = __ldg(D + s * dstride + (size_t)i * n + kc);
   }
   double a1[NSPIN][KC], a2[NSPIN][2], jq[KC][2];
 #pragma unroll
@@ -588,36 +526,134 @@ jk_packed_tma_kernel(const double* __restrict__ eri, const uint64_t* __restrict_
 #pragma unroll
   for (int s = 0; s < NSPIN; ++s) a2[s][0] = a2[s][1] = 0.0;
 
-  const double2* my = reinterpret_cast<const double2*>(ring) + m;  // + s*KC*LW/2 + t*LW/2
-  int j = j_first;
+  const int rows = i + 1;
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) mbar_init(bars + d, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  // lane 0 only: post the copies of row (i,j) into `stage`
+  auto issue_row = [&](int stage, const double* row, int j) {
+    double* dst = stages + stage * STG;
+    uint64_t* bar = bars + stage;
+    uint32_t len[KC], total = NSPIN * (64 + KC);
+#pragma unroll
+    for (int t = 0; t < KC; ++t) {
+      const int k = k0 + t;
+      if (MODE == 0) {
+        len[t] = 64;
+      } else {
+        // stored (padded) length of segment k of row (i,j), clipped to this warp's l window
+        int seg = k > i ? 0 : ((k < i ? k : j) + 2) & ~1;
+        seg -= wl;
+        len[t] = seg <= 0 ? 0u : (uint32_t)(seg < 64 ? seg : 64);
+      }
+      total += len[t];
+    }
+    mbar_expect_tx(bar, total * 8u);
+#pragma unroll
+    for (int t = 0; t < KC; ++t)
+      if (MODE == 0 || len[t])
+        bulk_g2s(dst + t * 64, row + seg_off(min(k0 + t, i)) + wl, len[t] * 8u, bar);
+#pragma unroll
+    for (int s = 0; s < NSPIN; ++s) {
+      const double* dj = D + s * dstride + (size_t)j * n;
+      bulk_g2s(dst + KC * 64 + s * 64, dj + wl, 512u, bar);
+      bulk_g2s(dst + KC * 64 + NSPIN * 64 + s * KC, dj + k0, KC * 8u, bar);
+    }
+  };
+
+  const int j_first = (int)(rot % (uint32_t)rows);
+  int j = j_first;  // load side
+  const double* row = eri_i + (uint64_t)j * Ei + seg_off(j);
+  int jc = j_first;  // consume side
+  double* kj0 = Kp + (size_t)jc * n;
+  int parked = 0, j_tile = jc;
+  double dp2 = __ldg(dq2 + Ei + jc);
+
+  const int red_r = lane / NV, red_v = lane - red_r * NV;
+  auto flush_tile = [&](int n_rows) {
+    __syncwarp();
+    if (red_r < n_rows) {
+      const double2* src = reinterpret_cast<const double2*>(ys + lane * YS);
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const double2 v = src[q];
+        acc0 += v.x;
+        acc1 += v.y;
+      }
+      const double tot = acc0 + acc1;
+      int jr = j_tile + red_r;
+      if (jr >= rows) jr -= rows;
+      if (red_v == NV - 1) {
+        atomicAdd(Jp + Ei + jr, tot);
+      } else {
+        const int sp = red_v / KC, t = red_v - sp * KC;
+        if (MODE == 0 || k0 + t <= i) atomicAdd(Kp + sp * dstride + (size_t)jr * n + k0 + t, tot);
+      }
+    }
+    __syncwarp();
+  };
+
+  auto advance = [&]() {
+    if (j + 1 == rows) {
+      j = 0;
+      row = eri_i;
+    } else {
+      row += Ei + ((j + 2) & ~1);
+      ++j;
+    }
+  };
+
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; ++d)
+      if (d < rows) {
+        issue_row(d, row, j);
+        advance();
+      }
+  }
   for (int step = 0; step < rows; ++step) {
-    const int s = step % STAGES;
-    mbar_wait(full + s, (step / STAGES) & 1);
+    __syncwarp();  // every lane has finished reading the stage that is refilled next
+    if (lane == 0 && step + DEPTH - 1 < rows) {
+      issue_row((step + DEPTH - 1) % DEPTH, row, j);
+      advance();
+    }
+    const int jn = jc + 1 == rows ? 0 : jc + 1;
+    const double dp2_next = __ldg(dq2 + Ei + jn);
+    const int stage = step % DEPTH;
+    mbar_wait(bars + stage, (step / DEPTH) & 1);
+    const double* st = stages + stage * STG;
     double2 w[KC];
 #pragma unroll
     for (int t = 0; t < KC; ++t) {
-      const double2 v = my[(s * KC + t) * (LW / 2)];
-      // stale ring contents beyond the copied length are masked here
-      const bool valid = ok[t] && (!diag || k0 + t < i || l0 <= j);
+      const double2 v = reinterpret_cast<const double2*>(st + t * 64)[lane];
+      // bytes beyond the copied length are stale: select, never multiply
+      const bool valid = MODE == 0 ? true : (MODE == 2 ? (ok[t] && (k0 + t < i || l0 <= jc)) : ok[t]);
       w[t] = valid ? v : make_double2(0.0, 0.0);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty + s);  // stage is in registers: hand it back
-
-    const double dp2 = __ldg(dq2 + Ei + j);
     double dj_l[NSPIN][2], dj_k[NSPIN][KC];
 #pragma unroll
-    for (int sp = 0; sp < NSPIN; ++sp) {
-      const double* dj = D + sp * n2 + (size_t)j * n;
-      dj_l[sp][0] = __ldg(dj + lc);
-      dj_l[sp][1] = l1_in ? __ldg(dj + lc + 1) : 0.0;
+    for (int s = 0; s < NSPIN; ++s) {
+      const double2 v = reinterpret_cast<const double2*>(st + KC * 64 + s * 64)[lane];
+      dj_l[s][0] = v.x;
+      dj_l[s][1] = v.y;
+      const double* dk = st + KC * 64 + NSPIN * 64 + s * KC;  // broadcast reads
 #pragma unroll
-      for (int t = 0; t < KC; ++t) dj_k[sp][t] = __ldg(dj + min(k0 + t, i));
+      for (int t = 0; t < KC; t += 2) {
+        const double2 u = *reinterpret_cast<const double2*>(dk + t);
+        dj_k[s][t] = u.x;
+        dj_k[s][t + 1] = u.y;
+      }
     }
     double jp0 = 0.0, jp1 = 0.0;
-    double y[NSPIN][KC], z[NSPIN][2];
+    double z[NSPIN][2];
 #pragma unroll
-    for (int sp = 0; sp < NSPIN; ++sp) z[sp][0] = z[sp][1] = 0.0;
+    for (int s = 0; s < NSPIN; ++s) z[s][0] = z[s][1] = 0.0;
+    double* park = ys + parked * NV * YS + lane;
 #pragma unroll
     for (int t = 0; t < KC; ++t) {
       const double w0 = w[t].x, w1 = w[t].y;
@@ -626,45 +662,79 @@ jk_packed_tma_kernel(const double* __restrict__ eri, const uint64_t* __restrict_
       jq[t][0] = fma(w0, dp2, jq[t][0]);
       jq[t][1] = fma(w1, dp2, jq[t][1]);
 #pragma unroll
-      for (int sp = 0; sp < NSPIN; ++sp) {
-        a1[sp][t] = fma(w0, dj_l[sp][0], a1[sp][t]);
-        a1[sp][t] = fma(w1, dj_l[sp][1], a1[sp][t]);
-        a2[sp][0] = fma(w0, dj_k[sp][t], a2[sp][0]);
-        a2[sp][1] = fma(w1, dj_k[sp][t], a2[sp][1]);
-        y[sp][t] = fma(w1, di_l[sp][1], w0 * di_l[sp][0]);
-        z[sp][0] = fma(w0, di_k[sp][t], z[sp][0]);
-        z[sp][1] = fma(w1, di_k[sp][t], z[sp][1]);
+      for (int s = 0; s < NSPIN; ++s) {
+        a1[s][t] = fma(w0, dj_l[s][0], a1[s][t]);
+        a1[s][t] = fma(w1, dj_l[s][1], a1[s][t]);
+        a2[s][0] = fma(w0, dj_k[s][t], a2[s][0]);
+        a2[s][1] = fma(w1, dj_k[s][t], a2[s][1]);
+        park[(s * KC + t) * YS] = fma(w1, di_l[s][1], w0 * di_l[s][0]);  // -> K'[j,k]
+        z[s][0] = fma(w0, di_k[s][t], z[s][0]);
+        z[s][1] = fma(w1, di_k[s][t], z[s][1]);
       }
     }
-    const double jp = warp_sum(jp0 + jp1);
-    if (lane == 0) atomicAdd(Jp + Ei + j, jp);
+    park[(NV - 1) * YS] = jp0 + jp1;  // -> J~[pr(i,j)]
 #pragma unroll
-    for (int sp = 0; sp < NSPIN; ++sp) {
-      double* kj = Kp + sp * (n2 + DPAD) + (size_t)n * j;
-      if (l0_in) atomicAdd(kj + l0, z[sp][0]);  // K'[j,l]
-      if (l1_in) atomicAdd(kj + l0 + 1, z[sp][1]);
-      const double r = warp_transpose_reduce<KC>(y[sp], lane);
-      const int t = transpose_reduce_index<KC>(lane);
-      if (transpose_reduce_owner<KC>(lane) && k0 + t <= i) atomicAdd(kj + k0 + t, r);  // K'[j,k]
+    for (int s = 0; s < NSPIN; ++s) {
+      double* kj = kj0 + s * dstride;
+      if (l0_in) atomicAdd(kj + l0, z[s][0]);  // K'[j,l]
+      if (l1_in) atomicAdd(kj + l0 + 1, z[s][1]);
     }
-    j = j + 1 == rows ? 0 : j + 1;
+    if (++parked == RB) {
+      flush_tile(RB);
+      parked = 0;
+      j_tile = jn;
+    }
+    jc = jn;
+    kj0 = jn ? kj0 + n : Kp;
+    dp2 = dp2_next;
   }
+  if (parked) flush_tile(parked);
 
 #pragma unroll
-  for (int sp = 0; sp < NSPIN; ++sp) {
-    double* ki = Kp + sp * (n2 + DPAD) + (size_t)n * i;
-    if (l0_in) atomicAdd(ki + l0, a2[sp][0]);  // K'[i,l]
-    if (l1_in) atomicAdd(ki + l0 + 1, a2[sp][1]);
-    const double r = warp_transpose_reduce<KC>(a1[sp], lane);
+  for (int s = 0; s < NSPIN; ++s) {
+    double* ki = Kp + s * dstride + (size_t)n * i;
+    if (l0_in) atomicAdd(ki + l0, a2[s][0]);  // K'[i,l]
+    if (l1_in) atomicAdd(ki + l0 + 1, a2[s][1]);
+    const double r = warp_transpose_reduce<KC>(a1[s], lane);
     const int t = transpose_reduce_index<KC>(lane);
     if (transpose_reduce_owner<KC>(lane) && k0 + t <= i) atomicAdd(ki + k0 + t, r);  // K'[i,k]
   }
 #pragma unroll
   for (int t = 0; t < KC; ++t)
-    if (ok[t]) {
-      atomicAdd(Jp + joff[t], jq[t][0]);
-      atomicAdd(Jp + joff[t] + 1, jq[t][1]);
+    if (ok[t]) {  // J~[q]
+      double* jo = Jp + seg_off(min(k0 + t, i)) + lc;
+      atomicAdd(jo, jq[t][0]);
+      atomicAdd(jo + 1, jq[t][1]);
     }
+}
+
+// grid = (n_kchunks, n_i_owned, n_lblocks of 64), block = one warp.
+template <int NSPIN, int KC, int MINB>
+__global__ void __launch_bounds__(32, MINB)
+jk_packed_bulk_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Btab,
+                      uint64_t shard_offset, const double* __restrict__ D, size_t dstride,
+                      const double* __restrict__ dq2, double* __restrict__ Kp,
+                      double* __restrict__ Jp, int n, int i_lo) {
+  extern __shared__ __align__(128) unsigned char bk_smem[];
+  constexpr int TILE = packed_rb(NSPIN, KC) * (NSPIN * KC + 1) * YS;
+  double* ys = reinterpret_cast<double*>(bk_smem);
+  double* stages = ys + TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + DEPTH * bulk_stage_doubles(NSPIN, KC));
+  const int i = i_lo + blockIdx.y;
+  const int k0 = blockIdx.x * KC;
+  if (k0 > i) return;
+  const int wl = blockIdx.z * 64;
+  const int kmax = min(k0 + KC - 1, i);
+  if (wl > kmax) return;
+  const int lane = threadIdx.x;
+  const double* eri_i = eri + (Btab[i] - shard_offset);
+  const uint32_t rot = blockIdx.x * 40503u + blockIdx.z * 9973u + blockIdx.y * 17u;
+  if (kmax == i)
+    packed_item_bulk<NSPIN, KC, 2>(eri_i, D, dstride, dq2, Kp, Jp, ys, stages, bars, n, i, k0, wl, lane, rot);
+  else if (wl + 63 <= k0)
+    packed_item_bulk<NSPIN, KC, 0>(eri_i, D, dstride, dq2, Kp, Jp, ys, stages, bars, n, i, k0, wl, lane, rot);
+  else
+    packed_item_bulk<NSPIN, KC, 1>(eri_i, D, dstride, dq2, Kp, Jp, ys, stages, bars, n, i, k0, wl, lane, rot);
 }
 
 // dq2[seg_off(k) + l] = 2 * Dtot[k,l] for l <= k, pads = 0;  dpad = D with DPAD zeros appended
@@ -811,7 +881,7 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
   if (n_i > 0) {
     double* Jp = h->pk_acc;
     double* Kp = h->pk_acc + PQ;
-    static const int use_tma = [] {  // SCFB_PACKED_TMA=1 selects the bulk-copy ring (v3) kernel
+    static const int use_tma = [] {  // SCFB_PACKED_TMA=1 selects the bulk-copy (v4) kernel
       const char* v = std::getenv("SCFB_PACKED_TMA");
       return v ? std::atoi(v) : 0;
     }();
@@ -825,23 +895,23 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
     }();
     const int kc = kc_sel == 4 || kc_sel == 8 ? kc_sel : 8;
     if (use_tma && n % 2 == 0) {
-      dim3 tgrid((n + kc - 1) / kc, n_i, (n + LW - 1) / LW);
-      const size_t smem = (size_t)STAGES * kc * LW * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
-#define SCFB_PK_TMA(NS, KCV, MINB)                                                               \
+      dim3 bgrid((n + kc - 1) / kc, n_i, (n + 63) / 64);
+#define SCFB_PK_BULK(NS, KCV, MINB)                                                              \
   do {                                                                                           \
-    cudaFuncSetAttribute(jk_packed_tma_kernel<NS, KCV, MINB>,                                    \
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
-    jk_packed_tma_kernel<NS, KCV, MINB><<<tgrid, 32 * (CW + 1), smem, h->stream>>>(              \
-        h->eri, h->pk_btab, h->pk_offset, d_density, h->pk_dq2, Kp, Jp, n, h->i_lo);             \
+    const size_t sm_ = bulk_smem_bytes(NS, KCV);                                                 \
+    cudaFuncSetAttribute(jk_packed_bulk_kernel<NS, KCV, MINB>,                                   \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_);                 \
+    jk_packed_bulk_kernel<NS, KCV, MINB><<<bgrid, 32, sm_, h->stream>>>(                         \
+        h->eri, h->pk_btab, h->pk_offset, h->pk_dpad, dstride, h->pk_dq2, Kp, Jp, n, h->i_lo);   \
   } while (0)
-      if (n_spin == 1 && kc == 8) SCFB_PK_TMA(1, 8, 2);
-      else if (n_spin == 1) SCFB_PK_TMA(1, 4, 3);
-      else if (kc == 8) SCFB_PK_TMA(2, 8, 1);
-      else SCFB_PK_TMA(2, 4, 2);
-#undef SCFB_PK_TMA
+      if (n_spin == 1 && kc == 8) SCFB_PK_BULK(1, 8, 8);
+      else if (n_spin == 1) SCFB_PK_BULK(1, 4, 12);
+      else if (kc == 8) SCFB_PK_BULK(2, 8, 8);
+      else SCFB_PK_BULK(2, 4, 8);
+#undef SCFB_PK_BULK
       e = cudaGetLastError();
       if (e != cudaSuccess)
-        return scfb_fail(h, SCFB_ERR_CUDA, "jk_packed_tma_kernel launch: %s", cudaGetErrorString(e));
+        return scfb_fail(h, SCFB_ERR_CUDA, "jk_packed_bulk_kernel launch: %s", cudaGetErrorString(e));
       h->launches += 1;
       if (h->timed) cudaEventRecord(h->ev[1], h->stream);
       unpack_jk_kernel<<<148 * 2, 256, 0, h->stream>>>(h->pk_acc, h->pk_acc + PQ, h->jk, n, n_spin);
