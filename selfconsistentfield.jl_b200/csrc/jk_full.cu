@@ -16,6 +16,9 @@
 // (8 n^2 B each) are L2/L1 resident and re-read through the read-only path.
 #include "scfb_internal.h"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace {
 
 constexpr int TC = 8;          // c values per work item
@@ -219,6 +222,283 @@ jk_full_stream_kernel(const double* __restrict__ eri, const double* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K1 over the TMA engine (even n <= 512; the default there).  Same work item, same thread
+// mapping and the same epilogue as `jk_full_stream_kernel`, but nothing is prefetched through
+// registers.  A stage holds the G consecutive b-rows the CTA consumes together: per c-plane one
+// contiguous run of G*n doubles, the matching Dtot rows, and D_s[c0..c0+8, b] per row and spin.
+// Each of these is ONE 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on the stage's
+// "full" mbarrier, posted by lane 0 of four producer warps (a bulk copy costs its issuer ~35
+// instructions / ~70 cycles, see benchmarks/micro/bulk_copy_rate.cu; 8 consumer warps + 1..4
+// producers are allocated as 12 warps anyway).  The consumer warps copy their operands out with
+// LDS.128, release the stage through the "empty" mbarrier and do the FMAs.  Bytes in flight are
+// bounded by shared memory (2 CTAs x S=3 stages x ~36 KB per SM) instead of by the register
+// file (64 KB per SM for the LDG version), which is what a 7+ TB/s read stream needs.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u)  // suspend-time hint (ns): fewer spins
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+constexpr int TMA_MAX_STAGES = 4;
+__host__ __device__ inline size_t tma_stage_doubles(int n, int G, int n_spin) {
+  return (size_t)(TC + 1) * G * n + (size_t)G * n_spin * TC;
+}
+
+constexpr int TMA_PRODUCERS = 4;  // producer warps per CTA (9..12 warps are allocated as 12 anyway)
+
+// grid = (n_chunks, n_slabs, BS); block = 32 * (consumer warps + TMA_PRODUCERS); smem = S stages.
+template <int NSPIN>
+__global__ void __launch_bounds__(MAX_THREADS + 32 * TMA_PRODUCERS, 2)
+jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dtot,
+                   const double* __restrict__ dens, double* __restrict__ jk,
+                   double* __restrict__ kpart, double* __restrict__ jpart, int n, int nu_lo, int R,
+                   int G, int S) {
+  extern __shared__ __align__(128) double ring[];  // [S][stage]; reused as kred[G][NSPIN][n]
+  __shared__ double jred[MAX_THREADS / 32][TC];
+  __shared__ uint64_t full[TMA_MAX_STAGES], empty[TMA_MAX_STAGES];
+
+  const int tid = threadIdx.x;
+  constexpr int CW = MAX_THREADS / 32;  // consumer warps (those beyond R*G threads only keep the barriers going)
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool producer = warp >= CW;
+  const int g = tid / R;
+  const int r = tid - g * R;
+  const bool active = !producer && g < G;  // (tid / R >= G for consumer threads beyond R*G)
+  const int a0 = r * 2;
+  const int chunk = blockIdx.x, n_chunks = gridDim.x, slab = blockIdx.y;
+  const int c0 = chunk * TC;
+  const int tcn = min(TC, n - c0);
+  const size_t n2 = (size_t)n * n;
+  const int BS = gridDim.z, bz = blockIdx.z;
+  const int nb = (n + BS - 1) / BS;
+  const int b_lo = bz * nb, b_hi = min(n, b_lo + nb);
+  const int n_iter = (b_hi - b_lo + G - 1) / G;
+  const size_t stage_doubles = tma_stage_doubles(n, G, NSPIN);
+  const int Gn = G * n;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, TMA_PRODUCERS);
+      mbar_init(empty + s, CW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // Register budget: the CTA is launched with 80 registers per thread (2 CTAs x 384 threads); the
+  // producer warpgroup gives back all but 32, the two consumer warpgroups grow to 104.
+  if (producer) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    // Copy jobs of one stage, dealt round-robin to the producer warps (job J -> warp J % 4):
+    //   J < tcn       plane c0+J, rows*n doubles                         -> slot J of the stage
+    //   J == tcn      the Dtot rows, rows*n doubles                      -> slot TC
+    //   J = tcn+1+q   D_s[c0..c0+tcn, b+gg], q = gg*NSPIN+sp, tcn doubles -> the stage's tail
+    //                 (n even => tcn even => a multiple of 16 bytes)
+    // Lane 0 posts its jobs, then announces their byte count on the stage's "full" barrier (4
+    // arrivals + the bytes complete a phase; the phase cannot complete before all four have
+    // arrived, so copies that land before the announcement are accounted for).  Every source
+    // address advances by G*n doubles per stage: the pointers of a warp's first MAXMINE jobs
+    // live in registers and a copy costs an add plus the UBLKCP sequence (~35 instructions) —
+    // kept out of the consumers' instruction stream, which is what made the first, consumer-posted
+    // version instruction-bound (8.5 ms).
+    if (lane == 0) {
+      const int pw = warp - CW;
+      const double* xbase = eri + ((size_t)slab * n + c0) * n2 + (size_t)b_lo * n;  // plane c0, row b_lo
+      const int n_jobs = tcn + 1 + G * NSPIN;
+      auto job_src = [&](int J) -> const double* {
+        if (J < tcn) return xbase + (size_t)J * n2;
+        if (J == tcn) return dtot + (size_t)b_lo * n;
+        const int q = J - tcn - 1, gg = q / NSPIN, sp = q - gg * NSPIN;
+        return dens + sp * n2 + (size_t)(b_lo + gg) * n + c0;
+      };
+      auto job_dst = [&](int J) -> int {
+        return J < tcn ? J * Gn : (J == tcn ? TC * Gn : (TC + 1) * Gn + (J - tcn - 1) * TC);
+      };
+      constexpr int MAXMINE = 4;
+      const double* jsrc[MAXMINE];
+      int jdst[MAXMINE], jrow[MAXMINE];  // jrow: -1 = row-sized job, else the row gg of a small job
+#pragma unroll
+      for (int k = 0; k < MAXMINE; ++k) {
+        const int J = pw + k * TMA_PRODUCERS;
+        jsrc[k] = J < n_jobs ? job_src(J) : nullptr;
+        jdst[k] = J < n_jobs ? job_dst(J) : 0;
+        jrow[k] = J <= tcn ? -1 : (J - tcn - 1) / NSPIN;
+      }
+      const uint32_t small_bytes = (uint32_t)tcn * 8u;
+      int s = 0;
+      uint32_t parity = 1;  // a fresh "empty" barrier passes a wait on the opposite parity
+      double* dst = ring;
+      for (int it = 0; it < n_iter; ++it) {
+        mbar_wait(empty + s, parity);
+        const int rows = min(G, b_hi - (b_lo + it * G));
+        const uint32_t row_bytes = (uint32_t)(rows * n) * 8u;
+        uint64_t* bar = full + s;
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int k = 0; k < MAXMINE; ++k) {
+          if (jsrc[k] != nullptr) {
+            if (jrow[k] < 0) {
+              bulk_g2s(dst + jdst[k], jsrc[k], row_bytes, bar);
+              bytes += row_bytes;
+            } else if (jrow[k] < rows) {
+              bulk_g2s(dst + jdst[k], jsrc[k], small_bytes, bar);
+              bytes += small_bytes;
+            }
+            jsrc[k] += Gn;
+          }
+        }
+        for (int J = pw + MAXMINE * TMA_PRODUCERS; J < n_jobs; J += TMA_PRODUCERS) {  // small n only
+          const bool big = J <= tcn;
+          if (big || (J - tcn - 1) / NSPIN < rows) {
+            bulk_g2s(dst + job_dst(J), job_src(J) + (size_t)it * Gn, big ? row_bytes : small_bytes, bar);
+            bytes += big ? row_bytes : small_bytes;
+          }
+        }
+        mbar_expect_tx(bar, bytes);
+        dst += stage_doubles;
+        if (++s == S) {
+          s = 0;
+          parity ^= 1;
+          dst = ring;
+        }
+      }
+    }
+    return;  // the epilogue synchronises the consumer threads only (named barrier 1)
+  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+  double jacc[TC];
+  double kacc[NSPIN][2];
+#pragma unroll
+  for (int t = 0; t < TC; ++t) jacc[t] = 0.0;
+#pragma unroll
+  for (int s = 0; s < NSPIN; ++s) kacc[s][0] = kacc[s][1] = 0.0;
+  {
+    // per-thread operand offsets inside a stage (doubles)
+    const int x_off = g * n + a0;
+    const int ds_off = (TC + 1) * Gn + g * NSPIN * TC;
+    int s = 0;
+    uint32_t parity = 0;
+    const double* st = ring;
+    int b = b_lo + g;
+    for (int it = 0; it < n_iter; ++it) {
+      mbar_wait(full + s, parity);
+      const bool live = active && b < b_hi;
+      double2 x[TC], dt = make_double2(0.0, 0.0);
+      double ds[NSPIN][TC];
+      if (live) {
+        const double* xp = st + x_off;
+#pragma unroll
+        for (int t = 0; t < TC; ++t) {
+          x[t] = t < tcn ? *reinterpret_cast<const double2*>(xp) : make_double2(0.0, 0.0);
+          xp += Gn;
+        }
+        dt = *reinterpret_cast<const double2*>(xp);  // slot TC: the Dtot rows
+        const double* dsp = st + ds_off;             // broadcast reads
+#pragma unroll
+        for (int sp = 0; sp < NSPIN; ++sp)
+#pragma unroll
+          for (int t = 0; t < TC; t += 2) {
+            const double2 d2 = *reinterpret_cast<const double2*>(dsp + sp * TC + t);
+            ds[sp][t] = d2.x;
+            ds[sp][t + 1] = d2.y;
+          }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);  // operands are in registers: hand the stage back
+      if (live) {
+#pragma unroll
+        for (int t = 0; t < TC; ++t) {
+          jacc[t] = fma(x[t].x, dt.x, jacc[t]);
+          jacc[t] = fma(x[t].y, dt.y, jacc[t]);
+#pragma unroll
+          for (int sp = 0; sp < NSPIN; ++sp) {
+            // columns of D beyond the last chunk's tcn are never copied: mask instead of multiply
+            const double d = t < tcn ? ds[sp][t] : 0.0;
+            kacc[sp][0] = fma(x[t].x, d, kacc[sp][0]);
+            kacc[sp][1] = fma(x[t].y, d, kacc[sp][1]);
+          }
+        }
+      }
+      b += G;
+      st += stage_doubles;
+      if (++s == S) {
+        s = 0;
+        parity ^= 1;
+        st = ring;
+      }
+    }
+  }
+
+  // ---- epilogue: identical to jk_full_stream_kernel (ring reused as kred) ----
+  double* kred = ring;
+#pragma unroll
+  for (int t = 0; t < TC; ++t) {
+    double v = warp_sum(jacc[t]);
+    if (lane == 0) jred[warp][t] = v;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");  // every stage consumed: ring is free
+  if (G > 1 && active) {
+#pragma unroll
+    for (int s = 0; s < NSPIN; ++s) {
+      kred[((size_t)g * NSPIN + s) * n + a0] = kacc[s][0];
+      kred[((size_t)g * NSPIN + s) * n + a0 + 1] = kacc[s][1];
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
+  const size_t item = ((size_t)slab * n_chunks + chunk) * BS + bz;
+  if (tid < tcn) {
+    double v = 0.0;
+    for (int w = 0; w < CW; ++w) v += jred[w][tid];
+    if (BS == 1)
+      jk[(size_t)(nu_lo + slab) * n + c0 + tid] = v;
+    else
+      jpart[item * TC + tid] = v;
+  }
+  double* kp = kpart + item * NSPIN * n;
+  if (G > 1) {
+    for (int i = tid; i < NSPIN * n; i += MAX_THREADS) {
+      double v = 0.0;
+      for (int gg = 0; gg < G; ++gg) v += kred[(size_t)gg * NSPIN * n + i];
+      kp[i] = v;
+    }
+  } else if (active) {
+#pragma unroll
+    for (int s = 0; s < NSPIN; ++s) {
+      kp[(size_t)s * n + a0] = kacc[s][0];
+      kp[(size_t)s * n + a0 + 1] = kacc[s][1];
+    }
+  }
+}
+
 // K[a, nu, s] = sum over (chunk, b-split) of the partial rows; with b-splits also
 // J[c, nu] = sum over the b-splits.  Fixed order -> deterministic.
 __global__ void k_reduce_kernel(const double* __restrict__ kpart, const double* __restrict__ jpart,
@@ -254,6 +534,45 @@ __global__ void accumulate_kernel(const double* __restrict__ jk, double* __restr
     const size_t s = i / n2, e = i - s * n2;
     out[i] += jk[e] - jk[(1 + s) * n2 + e];
   }
+}
+
+template <int NSPIN>
+cudaError_t launch_tma(scfb_handle_s* h, const double* d_density, const double* d_total) {
+  const int n = h->n;
+  const int n_slabs = h->nu_hi - h->nu_lo;
+  const int n_chunks = (n + TC - 1) / TC;
+  const int R = n / 2;
+  int G = 256 / R;
+  if (G < 1) G = 1;
+  if (G > n) G = n;
+  const size_t stage = tma_stage_doubles(n, G, NSPIN) * sizeof(double);
+  // two CTAs per SM share 227 KB (1 KB per CTA is reserved, ~0.6 KB static)
+  int S = (int)((size_t)(113 * 1024 - 2048) / stage);
+  if (S > TMA_MAX_STAGES) S = TMA_MAX_STAGES;
+  if (S < 2) S = 2;
+  const size_t smem = (size_t)S * stage;
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[NSPIN]) {
+    cudaError_t e = cudaFuncSetAttribute(jk_full_tma_kernel<NSPIN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    if (e == cudaSuccess)  // two CTAs only fit with the largest shared-memory carveout
+      e = cudaFuncSetAttribute(jk_full_tma_kernel<NSPIN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    attr_set[NSPIN] = true;
+  }
+  static const bool verbose = std::getenv("SCFB_VERBOSE") != nullptr;
+  if (verbose) {
+    int occ = 0, occ0 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jk_full_tma_kernel<NSPIN>, MAX_THREADS + 32 * TMA_PRODUCERS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, jk_full_tma_kernel<NSPIN>, MAX_THREADS + 32 * TMA_PRODUCERS, 0);
+    fprintf(stderr, "[scfb] jk_full_tma_kernel<%d>: n=%d R=%d G=%d stages=%d smem=%zu B threads=%d CTAs/SM=%d "
+            "(%d without dynamic smem)\n", NSPIN, n, R, G, S, smem, MAX_THREADS + 32 * TMA_PRODUCERS, occ, occ0);
+  }
+  dim3 grid(n_chunks, n_slabs, h->b_splits);
+  jk_full_tma_kernel<NSPIN><<<grid, MAX_THREADS + 32 * TMA_PRODUCERS, smem, h->stream>>>(
+      h->eri, d_total, d_density, h->jk, h->kpart, h->jpart, n, h->nu_lo, R, G, S);
+  return cudaGetLastError();
 }
 
 template <int VEC, int NSPIN, int MAXT>
@@ -310,7 +629,13 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
   cudaError_t e;
   if (h->timed) cudaEventRecord(h->ev[3], h->stream);
   const bool wide = (even ? n / 2 : n) > MAX_THREADS;  // rows longer than one 256-thread pass
-  if (even && !wide)
+  static const int use_tma = [] {  // SCFB_FULL_TMA=0 selects the register-prefetch (LDG) kernel
+    const char* v = std::getenv("SCFB_FULL_TMA");
+    return v ? std::atoi(v) : 1;
+  }();
+  if (use_tma && even && !wide && n >= 8)
+    e = n_spin == 1 ? launch_tma<1>(h, d_density, d_total) : launch_tma<2>(h, d_density, d_total);
+  else if (even && !wide)
     e = n_spin == 1 ? launch_stream<2, 1, 256>(h, d_density, d_total)
                     : launch_stream<2, 2, 256>(h, d_density, d_total);
   else if (even)
