@@ -73,7 +73,17 @@ def measured_traffic(a, world):
     if not os.path.exists(path) or world != 1:
         return None
     key = f"{a.layout}_n{a.n_bas}_spin{a.n_spin}"
+    if a.layout == "full" and dominant_kernel(a) == "jk_full_stream_kernel":
+        key += "_ldg"
     return json.load(open(path)).get(key, {}).get("dram_bytes_per_launch")
+
+
+def dominant_kernel(a):
+    """Name of the kernel the roofline object describes (same selection rule as csrc/jk_full.cu)."""
+    if a.layout != "full":
+        return "jk_packed_kernel"
+    tma = os.environ.get("SCFB_FULL_TMA", "1") != "0" and a.n_bas % 2 == 0 and 8 <= a.n_bas <= 512
+    return "jk_full_tma_kernel" if tma else "jk_full_stream_kernel"
 
 
 def peaks():
@@ -353,7 +363,7 @@ def run_ours(a, rank, local_rank, world):
                        "l2_policy": "inputs (ERI shard) far larger than the 126 MB L2; no flush"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic(a, world),
-                         "kernel": "jk_full_stream_kernel" if a.layout == "full" else "jk_packed_kernel",
+                         "kernel": dominant_kernel(a),
                          "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": launch_bytes, "peak_source": peak_src,
                          "kernel_share_of_step": k_ms / (ms / a.steps)},
