@@ -135,3 +135,40 @@ def test_packed_fullsize_properties(packed_builder):
     j3, k3 = b.jk(da[:, :, None], 2 * da)
     assert np.abs(j3 - j1).max() < 1e-13 * np.abs(j1).max()
     assert np.abs(k3 - k1).max() < 1e-13 * np.abs(k1).max()
+
+
+def test_n512_shard_known_answers_and_linearity():
+    """BASELINE.json config 5 (RHF n_bf=512, 550 GB over 8 GPUs): one rank's 68.7 GB shard
+    (rank 3 of 8, nu in [192, 256)) on a single GPU.  A rank without a communicator returns its
+    partial — the owned columns of J and K, zero elsewhere — which unit densities pin bit for bit
+    to the closed-form tensor elements; rows of 512 doubles are the longest the TMA kernel takes
+    (one b-row per stage)."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 75e9:
+        pytest.skip("needs 75 GB of free HBM")
+    n, rank, world = 512, 3, 8
+    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, rank=rank, n_ranks=world)
+    try:
+        lo, hi = b.shard_range
+        assert (lo, hi) == (192, 256) and b.eri_bytes == 8 * n ** 3 * (hi - lo)
+        idx = np.arange(n)
+        own = idx[lo:hi]
+        for n_spin, (a0, b0), (a1, b1) in [(1, (3, 500), (511, 17)), (2, (256, 255), (0, 0))]:
+            total = unit(n, a0, b0)
+            density = np.stack([unit(n, a1, b1)] * n_spin, axis=2)
+            j, k = b.jk(density, total)
+            assert np.array_equal(j[:, lo:hi], synth.hash_eri_elements(a0, b0, idx[:, None], own[None, :]))
+            ref_k = synth.hash_eri_elements(idx[:, None], b1, a1, own[None, :])
+            for s in range(n_spin):
+                assert np.array_equal(k[:, lo:hi, s], ref_k)
+            assert not j[:, :lo].any() and not j[:, hi:].any() and not k[:, :lo].any() and not k[:, hi:].any()
+        da = synth.hash_symmetric_matrix(n, synth.SEED_DA)
+        w = synth.hash_symmetric_matrix(n, 99)
+        j1, k1 = b.jk(da[:, :, None], 2 * da)
+        jw, kw = b.jk(w[:, :, None], w)
+        j2, k2 = b.jk((da - 2 * w)[:, :, None], 2 * da + 3 * w)
+        assert np.abs(j2 - (j1 + 3 * jw)).max() < 1e-12 * np.abs(j2).max()
+        assert np.abs(k2 - (k1 - 2 * kw)).max() < 1e-12 * np.abs(k2).max()
+    finally:
+        b.close()
