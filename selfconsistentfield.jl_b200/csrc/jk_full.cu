@@ -21,6 +21,10 @@
 
 namespace {
 
+#ifndef SCFB_TMA_WAIT_HINT
+#define SCFB_TMA_WAIT_HINT 20000u  // mbarrier.try_wait suspend-time hint, ns
+#endif
+
 constexpr int TC = 8;          // c values per work item
 constexpr int MAX_THREADS = 256;
 
@@ -230,10 +234,12 @@ jk_full_stream_kernel(const double* __restrict__ eri, const double* __restrict__
 // Each of these is ONE 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on the stage's
 // "full" mbarrier, posted by lane 0 of four producer warps (a bulk copy costs its issuer ~35
 // instructions / ~70 cycles, see benchmarks/micro/bulk_copy_rate.cu; 8 consumer warps + 1..4
-// producers are allocated as 12 warps anyway).  The consumer warps copy their operands out with
-// LDS.128, release the stage through the "empty" mbarrier and do the FMAs.  Bytes in flight are
-// bounded by shared memory (2 CTAs x S=3 stages x ~36 KB per SM) instead of by the register
-// file (64 KB per SM for the LDG version), which is what a 7+ TB/s read stream needs.
+// producers are allocated as 12 warps anyway).  The consumer warps read their operands with
+// LDS.128 (four planes at a time, D_s pair by pair: 80 registers, no spills), do the FMAs and
+// release the stage through the "empty" mbarrier.  Bytes in flight are bounded by shared memory
+// (2 CTAs x S=3 stages x ~36 KB per SM) instead of by the register file (64 KB per SM for the
+// LDG version), which is what a 7+ TB/s read stream needs.  CTAs are persistent and draw work
+// items from a global counter, so the ring keeps running across item boundaries.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -257,7 +263,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
-      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u)  // suspend-time hint (ns): fewer spins
+      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(SCFB_TMA_WAIT_HINT)  // suspend-time hint (ns): fewer spins
       : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -269,55 +275,81 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 constexpr int TMA_MAX_STAGES = 4;
+// position of a work item's partial rows in kpart / jpart (the order k_reduce_kernel sums in)
+__device__ __forceinline__ size_t item_index(int chunk, int slab, int bz, int n_chunks, int BS) {
+  return ((size_t)slab * n_chunks + chunk) * BS + bz;
+}
 __host__ __device__ inline size_t tma_stage_doubles(int n, int G, int n_spin) {
   return (size_t)(TC + 1) * G * n + (size_t)G * n_spin * TC;
 }
 
 constexpr int TMA_PRODUCERS = 4;  // producer warps per CTA (9..12 warps are allocated as 12 anyway)
 
-// grid = (n_chunks, n_slabs, BS); block = 32 * (consumer warps + TMA_PRODUCERS); smem = S stages.
+// Persistent: grid = min(items, 2 * SMs) CTAs drawing work items from a global counter, where
+// item = chunk + n_chunks * (slab + n_slabs * bz).  The stage ring runs on ACROSS items: while
+// the consumers finish an item (J/K reductions, partial-row stores) the producers are already S-1
+// stages into the next one, so the ring's fill latency and the epilogue are paid once per CTA, not
+// once per item (measured per-item bubble of the one-item-per-CTA version: ~5 us).
+// block = MAX_THREADS consumer threads + 32 * TMA_PRODUCERS; dynamic smem = S stages.
 template <int NSPIN>
 __global__ void __launch_bounds__(MAX_THREADS + 32 * TMA_PRODUCERS, 2)
 jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dtot,
                    const double* __restrict__ dens, double* __restrict__ jk,
                    double* __restrict__ kpart, double* __restrict__ jpart, int n, int nu_lo, int R,
-                   int G, int S) {
-  extern __shared__ __align__(128) double ring[];  // [S][stage]; reused as kred[G][NSPIN][n]
+                   int G, int S, int n_chunks, int n_slabs, int BS, int* __restrict__ sched) {
+  extern __shared__ __align__(128) double ring[];  // [S][stage]
   __shared__ double jred[MAX_THREADS / 32][TC];
   __shared__ uint64_t full[TMA_MAX_STAGES], empty[TMA_MAX_STAGES];
+  // Work items are handed out dynamically (SMs do not all stream at the same rate: a static
+  // round-robin was 6 % slower than one CTA per item).  Lane 0 of producer warp 0 draws the CTA's
+  // next item from a global counter and publishes it in a two-deep queue; the other producers and
+  // the consumer warps pick it up from there.  -1 ends the CTA.
+  __shared__ int item_q[2];
+  __shared__ uint64_t item_full[2], item_empty[2];
 
   const int tid = threadIdx.x;
   constexpr int CW = MAX_THREADS / 32;  // consumer warps (those beyond R*G threads only keep the barriers going)
   const int warp = tid >> 5, lane = tid & 31;
   const bool producer = warp >= CW;
-  const int g = tid / R;
-  const int r = tid - g * R;
-  const bool active = !producer && g < G;  // (tid / R >= G for consumer threads beyond R*G)
-  const int a0 = r * 2;
-  const int chunk = blockIdx.x, n_chunks = gridDim.x, slab = blockIdx.y;
-  const int c0 = chunk * TC;
-  const int tcn = min(TC, n - c0);
   const size_t n2 = (size_t)n * n;
-  const int BS = gridDim.z, bz = blockIdx.z;
   const int nb = (n + BS - 1) / BS;
-  const int b_lo = bz * nb, b_hi = min(n, b_lo + nb);
-  const int n_iter = (b_hi - b_lo + G - 1) / G;
   const size_t stage_doubles = tma_stage_doubles(n, G, NSPIN);
   const int Gn = G * n;
+  const int n_items = n_chunks * n_slabs * BS;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, TMA_PRODUCERS);
       mbar_init(empty + s, CW);
     }
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(item_full + q, 1);
+      mbar_init(item_empty + q, CW + TMA_PRODUCERS - 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  // k-th item of this CTA: slot k & 1, phase (k >> 1) & 1
+  auto publish_item = [&](int k) {  // scheduler only
+    if (k >= 2) mbar_wait(item_empty + (k & 1), ((k >> 1) & 1) ^ 1);
+    int item = k == 0 ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(sched, 1);
+    if (item >= n_items) item = -1;
+    item_q[k & 1] = item;
+    mbar_arrive(item_full + (k & 1));  // release: the store above is visible to the waiters
+    return item;
+  };
+  auto fetch_item = [&](int k) {  // everyone else; one arrival per warp on item_empty
+    mbar_wait(item_full + (k & 1), (k >> 1) & 1);
+    const int item = item_q[k & 1];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(item_empty + (k & 1));
+    return item;
+  };
 
-  // Register budget: the CTA is launched with 80 registers per thread (2 CTAs x 384 threads); the
-  // producer warpgroup gives back all but 32, the two consumer warpgroups grow to 104.
+  // Register budget: 80 per thread (2 CTAs x 384 threads).  The consumers fit because D_s is read
+  // from the stage pair by pair inside the FMA loop instead of being preloaded (a setmaxnreg
+  // split 32/104 measured the same, but left the 32-register producers spilling).
   if (producer) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     // Copy jobs of one stage, dealt round-robin to the producer warps (job J -> warp J % 4):
     //   J < tcn       plane c0+J, rows*n doubles                         -> slot J of the stage
     //   J == tcn      the Dtot rows, rows*n doubles                      -> slot TC
@@ -332,121 +364,152 @@ jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dt
     // version instruction-bound (8.5 ms).
     if (lane == 0) {
       const int pw = warp - CW;
-      const double* xbase = eri + ((size_t)slab * n + c0) * n2 + (size_t)b_lo * n;  // plane c0, row b_lo
-      const int n_jobs = tcn + 1 + G * NSPIN;
-      auto job_src = [&](int J) -> const double* {
-        if (J < tcn) return xbase + (size_t)J * n2;
-        if (J == tcn) return dtot + (size_t)b_lo * n;
-        const int q = J - tcn - 1, gg = q / NSPIN, sp = q - gg * NSPIN;
-        return dens + sp * n2 + (size_t)(b_lo + gg) * n + c0;
-      };
-      auto job_dst = [&](int J) -> int {
-        return J < tcn ? J * Gn : (J == tcn ? TC * Gn : (TC + 1) * Gn + (J - tcn - 1) * TC);
-      };
-      constexpr int MAXMINE = 4;
-      const double* jsrc[MAXMINE];
-      int jdst[MAXMINE], jrow[MAXMINE];  // jrow: -1 = row-sized job, else the row gg of a small job
-#pragma unroll
-      for (int k = 0; k < MAXMINE; ++k) {
-        const int J = pw + k * TMA_PRODUCERS;
-        jsrc[k] = J < n_jobs ? job_src(J) : nullptr;
-        jdst[k] = J < n_jobs ? job_dst(J) : 0;
-        jrow[k] = J <= tcn ? -1 : (J - tcn - 1) / NSPIN;
-      }
-      const uint32_t small_bytes = (uint32_t)tcn * 8u;
       int s = 0;
       uint32_t parity = 1;  // a fresh "empty" barrier passes a wait on the opposite parity
       double* dst = ring;
-      for (int it = 0; it < n_iter; ++it) {
-        mbar_wait(empty + s, parity);
-        const int rows = min(G, b_hi - (b_lo + it * G));
-        const uint32_t row_bytes = (uint32_t)(rows * n) * 8u;
-        uint64_t* bar = full + s;
-        uint32_t bytes = 0;
+      for (int k = 0;; ++k) {
+        const int item = pw == 0 ? publish_item(k) : fetch_item(k);
+        if (item < 0) break;
+        const int chunk = item % n_chunks, rest = item / n_chunks;
+        const int slab = rest % n_slabs, bz = rest / n_slabs;
+        const int c0 = chunk * TC;
+        const int tcn = min(TC, n - c0);
+        const int b_lo = bz * nb, b_hi = min(n, b_lo + nb);
+        const int n_iter = (b_hi - b_lo + G - 1) / G;
+        const double* xbase = eri + ((size_t)slab * n + c0) * n2 + (size_t)b_lo * n;  // plane c0, row b_lo
+        const int n_jobs = tcn + 1 + G * NSPIN;
+        auto job_src = [&](int J) -> const double* {
+          if (J < tcn) return xbase + (size_t)J * n2;
+          if (J == tcn) return dtot + (size_t)b_lo * n;
+          const int q = J - tcn - 1, gg = q / NSPIN, sp = q - gg * NSPIN;
+          return dens + sp * n2 + (size_t)(b_lo + gg) * n + c0;
+        };
+        auto job_dst = [&](int J) -> int {
+          return J < tcn ? J * Gn : (J == tcn ? TC * Gn : (TC + 1) * Gn + (J - tcn - 1) * TC);
+        };
+        constexpr int MAXMINE = 4;
+        const double* jsrc[MAXMINE];
+        int jdst[MAXMINE], jrow[MAXMINE];  // jrow: -1 = row-sized job, else the row gg of a small job
 #pragma unroll
         for (int k = 0; k < MAXMINE; ++k) {
-          if (jsrc[k] != nullptr) {
-            if (jrow[k] < 0) {
-              bulk_g2s(dst + jdst[k], jsrc[k], row_bytes, bar);
-              bytes += row_bytes;
-            } else if (jrow[k] < rows) {
-              bulk_g2s(dst + jdst[k], jsrc[k], small_bytes, bar);
-              bytes += small_bytes;
+          const int J = pw + k * TMA_PRODUCERS;
+          jsrc[k] = J < n_jobs ? job_src(J) : nullptr;
+          jdst[k] = J < n_jobs ? job_dst(J) : 0;
+          jrow[k] = J <= tcn ? -1 : (J - tcn - 1) / NSPIN;
+        }
+        const uint32_t small_bytes = (uint32_t)tcn * 8u;
+        for (int it = 0; it < n_iter; ++it) {
+          mbar_wait(empty + s, parity);
+          const int rows = min(G, b_hi - (b_lo + it * G));
+          const uint32_t row_bytes = (uint32_t)(rows * n) * 8u;
+          uint64_t* bar = full + s;
+          uint32_t bytes = 0;
+#pragma unroll
+          for (int k = 0; k < MAXMINE; ++k) {
+            if (jsrc[k] != nullptr) {
+              if (jrow[k] < 0) {
+                bulk_g2s(dst + jdst[k], jsrc[k], row_bytes, bar);
+                bytes += row_bytes;
+              } else if (jrow[k] < rows) {
+                bulk_g2s(dst + jdst[k], jsrc[k], small_bytes, bar);
+                bytes += small_bytes;
+              }
+              jsrc[k] += Gn;
             }
-            jsrc[k] += Gn;
           }
-        }
-        for (int J = pw + MAXMINE * TMA_PRODUCERS; J < n_jobs; J += TMA_PRODUCERS) {  // small n only
-          const bool big = J <= tcn;
-          if (big || (J - tcn - 1) / NSPIN < rows) {
-            bulk_g2s(dst + job_dst(J), job_src(J) + (size_t)it * Gn, big ? row_bytes : small_bytes, bar);
-            bytes += big ? row_bytes : small_bytes;
+          for (int J = pw + MAXMINE * TMA_PRODUCERS; J < n_jobs; J += TMA_PRODUCERS) {  // small n only
+            const bool big = J <= tcn;
+            if (big || (J - tcn - 1) / NSPIN < rows) {
+              bulk_g2s(dst + job_dst(J), job_src(J) + (size_t)it * Gn, big ? row_bytes : small_bytes, bar);
+              bytes += big ? row_bytes : small_bytes;
+            }
           }
-        }
-        mbar_expect_tx(bar, bytes);
-        dst += stage_doubles;
-        if (++s == S) {
-          s = 0;
-          parity ^= 1;
-          dst = ring;
+          mbar_expect_tx(bar, bytes);
+          dst += stage_doubles;
+          if (++s == S) {
+            s = 0;
+            parity ^= 1;
+            dst = ring;
+          }
         }
       }
     }
-    return;  // the epilogue synchronises the consumer threads only (named barrier 1)
+    return;  // the consumers synchronise among themselves (named barrier 1)
   }
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-  double jacc[TC];
-  double kacc[NSPIN][2];
+
+  const int g = tid / R;
+  const int r = tid - g * R;
+  const bool active = g < G;  // (tid / R >= G for the consumer threads beyond R*G)
+  const int a0 = r * 2;
+  // per-thread operand offsets inside a stage (doubles)
+  const int x_off = g * n + a0;
+  const int ds_off = (TC + 1) * Gn + g * NSPIN * TC;
+  int s = 0;
+  uint32_t parity = 0;
+  const double* st = ring;
+
+  for (int k = 0;; ++k) {
+    const int item = fetch_item(k);
+    if (item < 0) break;
+    const int chunk = item % n_chunks, rest = item / n_chunks;
+    const int slab = rest % n_slabs, bz = rest / n_slabs;
+    const int c0 = chunk * TC;
+    const int tcn = min(TC, n - c0);
+    const int b_lo = bz * nb, b_hi = min(n, b_lo + nb);
+    const int n_iter = (b_hi - b_lo + G - 1) / G;
+
+    double jacc[TC];
+    double kacc[NSPIN][2];
 #pragma unroll
-  for (int t = 0; t < TC; ++t) jacc[t] = 0.0;
+    for (int t = 0; t < TC; ++t) jacc[t] = 0.0;
 #pragma unroll
-  for (int s = 0; s < NSPIN; ++s) kacc[s][0] = kacc[s][1] = 0.0;
-  {
-    // per-thread operand offsets inside a stage (doubles)
-    const int x_off = g * n + a0;
-    const int ds_off = (TC + 1) * Gn + g * NSPIN * TC;
-    int s = 0;
-    uint32_t parity = 0;
-    const double* st = ring;
+    for (int sp = 0; sp < NSPIN; ++sp) kacc[sp][0] = kacc[sp][1] = 0.0;
+
     int b = b_lo + g;
+    double* last_stage = nullptr;  // the item's last stage doubles as kred before it is released
+    int last_slot = 0;
     for (int it = 0; it < n_iter; ++it) {
       mbar_wait(full + s, parity);
       const bool live = active && b < b_hi;
-      double2 x[TC], dt = make_double2(0.0, 0.0);
-      double ds[NSPIN][TC];
       if (live) {
+        // two half-chunks of four planes: 16 operand registers live instead of 32
+        const double2 dt = *reinterpret_cast<const double2*>(st + x_off + TC * Gn);  // slot TC: Dtot rows
+        const double* dsp = st + ds_off;                                             // broadcast reads
         const double* xp = st + x_off;
 #pragma unroll
-        for (int t = 0; t < TC; ++t) {
-          x[t] = t < tcn ? *reinterpret_cast<const double2*>(xp) : make_double2(0.0, 0.0);
-          xp += Gn;
-        }
-        dt = *reinterpret_cast<const double2*>(xp);  // slot TC: the Dtot rows
-        const double* dsp = st + ds_off;             // broadcast reads
+        for (int h = 0; h < TC; h += 4) {
+          double2 x[4];
 #pragma unroll
-        for (int sp = 0; sp < NSPIN; ++sp)
-#pragma unroll
-          for (int t = 0; t < TC; t += 2) {
-            const double2 d2 = *reinterpret_cast<const double2*>(dsp + sp * TC + t);
-            ds[sp][t] = d2.x;
-            ds[sp][t + 1] = d2.y;
+          for (int t = 0; t < 4; ++t) {
+            x[t] = h + t < tcn ? *reinterpret_cast<const double2*>(xp) : make_double2(0.0, 0.0);
+            xp += Gn;
           }
+#pragma unroll
+          for (int t = 0; t < 4; t += 2) {
+            jacc[h + t] = fma(x[t].x, dt.x, jacc[h + t]);
+            jacc[h + t] = fma(x[t].y, dt.y, jacc[h + t]);
+            jacc[h + t + 1] = fma(x[t + 1].x, dt.x, jacc[h + t + 1]);
+            jacc[h + t + 1] = fma(x[t + 1].y, dt.y, jacc[h + t + 1]);
+#pragma unroll
+            for (int sp = 0; sp < NSPIN; ++sp) {
+              double2 d2 = *reinterpret_cast<const double2*>(dsp + sp * TC + h + t);
+              // columns of D beyond the last chunk's tcn are never copied: mask instead of multiply
+              if (h + t >= tcn) d2.x = 0.0;
+              if (h + t + 1 >= tcn) d2.y = 0.0;
+              kacc[sp][0] = fma(x[t].x, d2.x, kacc[sp][0]);
+              kacc[sp][1] = fma(x[t].y, d2.x, kacc[sp][1]);
+              kacc[sp][0] = fma(x[t + 1].x, d2.y, kacc[sp][0]);
+              kacc[sp][1] = fma(x[t + 1].y, d2.y, kacc[sp][1]);
+            }
+          }
+        }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty + s);  // operands are in registers: hand the stage back
-      if (live) {
-#pragma unroll
-        for (int t = 0; t < TC; ++t) {
-          jacc[t] = fma(x[t].x, dt.x, jacc[t]);
-          jacc[t] = fma(x[t].y, dt.y, jacc[t]);
-#pragma unroll
-          for (int sp = 0; sp < NSPIN; ++sp) {
-            // columns of D beyond the last chunk's tcn are never copied: mask instead of multiply
-            const double d = t < tcn ? ds[sp][t] : 0.0;
-            kacc[sp][0] = fma(x[t].x, d, kacc[sp][0]);
-            kacc[sp][1] = fma(x[t].y, d, kacc[sp][1]);
-          }
-        }
+      if (it + 1 < n_iter) {
+        if (lane == 0) mbar_arrive(empty + s);  // all reads of the stage are done: hand it back
+      } else {
+        last_stage = const_cast<double*>(st);
+        last_slot = s;
       }
       b += G;
       st += stage_doubles;
@@ -456,46 +519,62 @@ jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dt
         st = ring;
       }
     }
-  }
 
-  // ---- epilogue: identical to jk_full_stream_kernel (ring reused as kred) ----
-  double* kred = ring;
-#pragma unroll
-  for (int t = 0; t < TC; ++t) {
-    double v = warp_sum(jacc[t]);
-    if (lane == 0) jred[warp][t] = v;
-  }
-  asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");  // every stage consumed: ring is free
-  if (G > 1 && active) {
-#pragma unroll
-    for (int s = 0; s < NSPIN; ++s) {
-      kred[((size_t)g * NSPIN + s) * n + a0] = kacc[s][0];
-      kred[((size_t)g * NSPIN + s) * n + a0 + 1] = kacc[s][1];
+    if (n_iter == 0) {  // empty b-range of a split item: its partials are zero, no stage was used
+      if (tid < tcn) {
+        if (BS == 1)
+          jk[(size_t)(nu_lo + slab) * n + c0 + tid] = 0.0;
+        else
+          jpart[(size_t)item_index(chunk, slab, bz, n_chunks, BS) * TC + tid] = 0.0;
+      }
+      for (int i = tid; i < NSPIN * n; i += MAX_THREADS)
+        kpart[(size_t)item_index(chunk, slab, bz, n_chunks, BS) * NSPIN * n + i] = 0.0;
+      continue;
     }
-  }
-  asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
-  const size_t item = ((size_t)slab * n_chunks + chunk) * BS + bz;
-  if (tid < tcn) {
-    double v = 0.0;
-    for (int w = 0; w < CW; ++w) v += jred[w][tid];
-    if (BS == 1)
-      jk[(size_t)(nu_lo + slab) * n + c0 + tid] = v;
-    else
-      jpart[item * TC + tid] = v;
-  }
-  double* kp = kpart + item * NSPIN * n;
-  if (G > 1) {
-    for (int i = tid; i < NSPIN * n; i += MAX_THREADS) {
+    // ---- item epilogue (as in jk_full_stream_kernel; kred lives in the item's last stage) ----
+    double* kred = last_stage;  // [G][NSPIN][n]
+#pragma unroll
+    for (int t = 0; t < TC; ++t) {
+      double v = warp_sum(jacc[t]);
+      if (lane == 0) jred[warp][t] = v;
+    }
+    // every consumer has copied its operands out of the last stage and finished its FMAs
+    asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
+    if (G > 1 && active) {
+#pragma unroll
+      for (int sp = 0; sp < NSPIN; ++sp) {
+        kred[((size_t)g * NSPIN + sp) * n + a0] = kacc[sp][0];
+        kred[((size_t)g * NSPIN + sp) * n + a0 + 1] = kacc[sp][1];
+      }
+    }
+    if (tid < tcn) {
       double v = 0.0;
-      for (int gg = 0; gg < G; ++gg) v += kred[(size_t)gg * NSPIN * n + i];
-      kp[i] = v;
+      for (int w = 0; w < CW; ++w) v += jred[w][tid];
+      if (BS == 1)
+        jk[(size_t)(nu_lo + slab) * n + c0 + tid] = v;
+      else
+        jpart[(size_t)item_index(chunk, slab, bz, n_chunks, BS) * TC + tid] = v;
     }
-  } else if (active) {
+    double* kp = kpart + (size_t)item_index(chunk, slab, bz, n_chunks, BS) * NSPIN * n;
+    if (G > 1) {
+      asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
+      for (int i = tid; i < NSPIN * n; i += MAX_THREADS) {
+        double v = 0.0;
+        for (int gg = 0; gg < G; ++gg) v += kred[(size_t)gg * NSPIN * n + i];
+        kp[i] = v;
+      }
+    } else if (active) {
 #pragma unroll
-    for (int s = 0; s < NSPIN; ++s) {
-      kp[(size_t)s * n + a0] = kacc[s][0];
-      kp[(size_t)s * n + a0 + 1] = kacc[s][1];
+      for (int sp = 0; sp < NSPIN; ++sp) {
+        kp[(size_t)sp * n + a0] = kacc[sp][0];
+        kp[(size_t)sp * n + a0 + 1] = kacc[sp][1];
+      }
     }
+    // jred and kred are free again: release the last stage to the producers.  (The generic-proxy
+    // writes to kred are ordered before the async-proxy refill by the fence + barrier arrival.)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
+    if (lane == 0) mbar_arrive(empty + last_slot);
   }
 }
 
@@ -569,9 +648,25 @@ cudaError_t launch_tma(scfb_handle_s* h, const double* d_density, const double* 
     fprintf(stderr, "[scfb] jk_full_tma_kernel<%d>: n=%d R=%d G=%d stages=%d smem=%zu B threads=%d CTAs/SM=%d "
             "(%d without dynamic smem)\n", NSPIN, n, R, G, S, smem, MAX_THREADS + 32 * TMA_PRODUCERS, occ, occ0);
   }
-  dim3 grid(n_chunks, n_slabs, h->b_splits);
+  const long items = (long)n_chunks * n_slabs * h->b_splits;
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  static const int per_sm = [] {  // SCFB_FULL_TMA_CTAS=0: one CTA per item (non-persistent), else CTAs per SM
+    const char* v = std::getenv("SCFB_FULL_TMA_CTAS");
+    return v ? std::atoi(v) : 2;
+  }();
+  const long cap = per_sm > 0 ? (long)per_sm * n_sm : items;
+  const int grid = (int)(items < cap ? items : cap);
+  cudaError_t e = cudaMemsetAsync(h->sched, 0, sizeof(int), h->stream);
+  if (e != cudaSuccess) return e;
   jk_full_tma_kernel<NSPIN><<<grid, MAX_THREADS + 32 * TMA_PRODUCERS, smem, h->stream>>>(
-      h->eri, d_total, d_density, h->jk, h->kpart, h->jpart, n, h->nu_lo, R, G, S);
+      h->eri, d_total, d_density, h->jk, h->kpart, h->jpart, n, h->nu_lo, R, G, S, n_chunks, n_slabs,
+      h->b_splits, h->sched);
   return cudaGetLastError();
 }
 

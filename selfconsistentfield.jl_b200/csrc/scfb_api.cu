@@ -143,6 +143,7 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
   if (h->kpart_elems) CREATE_CUDA(cudaMalloc(&h->kpart, h->kpart_elems * sizeof(double)));
   if (layout == SCFB_LAYOUT_FULL && h->b_splits > 1)
     CREATE_CUDA(cudaMalloc(&h->jpart, scfb_jpart_elems_full(n_bas, h->nu_hi - h->nu_lo) * sizeof(double)));
+  CREATE_CUDA(cudaMalloc(&h->sched, sizeof(int)));
   if (layout == SCFB_LAYOUT_PACKED8) {
     const uint64_t PQ = scfb_packed_dq_elems(n_bas);
     CREATE_CUDA(cudaMalloc(&h->pk_acc, (PQ + 2 * (n2 + 64)) * sizeof(double)));
@@ -174,6 +175,7 @@ int scfb_destroy(scfb_handle_t h) {
   cudaFree(h->jk);
   cudaFree(h->kpart);
   cudaFree(h->jpart);
+  cudaFree(h->sched);
   cudaFree(h->pk_acc);
   cudaFree(h->pk_dq2);
   cudaFree(h->pk_dpad);

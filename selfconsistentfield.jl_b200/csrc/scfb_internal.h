@@ -38,6 +38,7 @@ struct scfb_handle_s {
   double* jk_sum = nullptr;     // allreduce result (n_ranks > 1); == jk when single rank
   double* kpart = nullptr;      // per-(nu, c-chunk, b-split) partial K rows
   double* jpart = nullptr;      // per-(nu, c-chunk, b-split) partial J values (b_splits > 1)
+  int* sched = nullptr;         // work-item counter of the persistent full-layout kernel
   int b_splits = 1;             // CTAs sharing one (nu, c-chunk) work item along b
   uint64_t kpart_elems = 0;
   double* h_stage = nullptr;    // pinned host staging, 5*n*n
