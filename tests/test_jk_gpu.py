@@ -245,6 +245,34 @@ def test_wide_rows_known_answers_on_a_shard(n, n_ranks):
     b.close()
 
 
+# ---- 1/8 shards of the bench sizes: the b-split grid (2-4 CTAs per work item) --------------------
+@pytest.mark.parametrize("n,rank", [(256, 5), (128, 7), (64, 0)])
+def test_eighth_shard_with_b_splits_known_answers(n, rank):
+    """What one GPU of eight runs at n_bf=256 / 128: so few equal-size work items that each is
+    split along b (csrc/jk_full.cu scfb_full_b_splits), J becomes a per-CTA partial too and the
+    persistent kernel's queue hands out chunk x slab x split items.  Unit densities pin the
+    owned columns bit for bit (UHF, so both K accumulators are exercised)."""
+    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, rank=rank, n_ranks=8)
+    lo, hi = b.shard_range
+    assert hi - lo == n // 8
+    idx, own = np.arange(n), np.arange(lo, hi)
+    unit = lambda a, c: (lambda m: (m.__setitem__((a, c), 1.0), m)[1])(np.zeros((n, n)))
+    for (a0, b0), (a1, b1), (a2, b2) in [((1, n - 2), (n - 1, 0), (n // 2, n // 2 + 1)),
+                                         ((n - 1, n - 1), (0, n - 1), (7, 8))]:
+        j, k = b.jk(np.stack([unit(a1, b1), unit(a2, b2)], axis=2), unit(a0, b0))
+        assert np.array_equal(j[:, lo:hi], synth.hash_eri_elements(a0, b0, idx[:, None], own[None, :]))
+        assert np.array_equal(k[:, lo:hi, 0], synth.hash_eri_elements(idx[:, None], b1, a1, own[None, :]))
+        assert np.array_equal(k[:, lo:hi, 1], synth.hash_eri_elements(idx[:, None], b2, a2, own[None, :]))
+        assert not j[:, :lo].any() and not j[:, hi:].any()
+    # dense densities: run-to-run bit-reproducibility of the fixed-order partial sums
+    da, db = synth.hash_symmetric_matrix(n, synth.SEED_DA), synth.hash_symmetric_matrix(n, synth.SEED_DB)
+    first = b.jk(np.stack([da, db], axis=2), da + db)
+    for _ in range(3):
+        again = b.jk(np.stack([da, db], axis=2), da + db)
+        assert np.array_equal(first[0], again[0]) and np.array_equal(first[1], again[1])
+    b.close()
+
+
 # ---- device-pointer twin on the caller's stream (what bench.py times) ------------------------
 @pytest.mark.parametrize("layout", ["full", "packed8"])
 def test_device_pointer_api_on_callers_stream(layout):
