@@ -689,11 +689,26 @@ cudaError_t launch_stream(scfb_handle_s* h, const double* d_density, const doubl
 
 }  // namespace
 
-// b-splits: equal-size work items fill 2 x 148 resident CTA slots in waves; below ~4 waves the
-// last, partly filled wave costs > 10 % (n_bf = 256 over 8 GPUs: 1024 items = 3.46 -> 4 waves).
+static bool tma_path(int n) {  // the selection rule of scfb_launch_jk_full
+  const char* v = std::getenv("SCFB_FULL_TMA");
+  return (v ? std::atoi(v) : 1) != 0 && n % 2 == 0 && n >= 8 && n / 2 <= MAX_THREADS;
+}
+
+// b-splits (gridDim.z / the third item coordinate): equal-size work items fill 2 x 148 resident
+// CTA slots in waves, and below ~4 waves the last, partly filled wave costs the LDG kernel > 10 %
+// (n_bf = 256 over 8 GPUs: 1024 items = 3.46 -> 4 waves), so it splits every item over 2-4 CTAs
+// along b.  The persistent TMA kernel hands items out dynamically and pays less per item; there
+// the split only adds partial rows (1/8 shard of n_bf = 256, whole build: 0.650 ms unsplit, 0.663
+// with 2, 0.686 with 4 splits; benchmarks/shard_bsplit.py), so it stays at 1.
+// SCFB_FULL_BSPLIT=1|2|4|8 overrides the rule; read at handle creation (tests, tuning).
 int scfb_full_b_splits(int n, int n_slabs) {
   const long items = (long)((n + TC - 1) / TC) * n_slabs;
   if (items <= 0) return 1;
+  if (const char* v = std::getenv("SCFB_FULL_BSPLIT")) {
+    const int forced = std::atoi(v);
+    if (forced > 0) return n / (2 * forced) >= 1 ? forced : 1;
+  }
+  if (tma_path(n)) return 1;
   int bs = 1;
   while (bs < 4 && items * bs < 4L * 2 * 148 && n / (2 * bs) >= 16) bs *= 2;
   return bs;
@@ -724,11 +739,7 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
   cudaError_t e;
   if (h->timed) cudaEventRecord(h->ev[3], h->stream);
   const bool wide = (even ? n / 2 : n) > MAX_THREADS;  // rows longer than one 256-thread pass
-  static const int use_tma = [] {  // SCFB_FULL_TMA=0 selects the register-prefetch (LDG) kernel
-    const char* v = std::getenv("SCFB_FULL_TMA");
-    return v ? std::atoi(v) : 1;
-  }();
-  if (use_tma && even && !wide && n >= 8)
+  if (tma_path(n))  // SCFB_FULL_TMA=0 selects the register-prefetch (LDG) kernel
     e = n_spin == 1 ? launch_tma<1>(h, d_density, d_total) : launch_tma<2>(h, d_density, d_total);
   else if (even && !wide)
     e = n_spin == 1 ? launch_stream<2, 1, 256>(h, d_density, d_total)

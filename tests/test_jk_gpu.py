@@ -246,12 +246,16 @@ def test_wide_rows_known_answers_on_a_shard(n, n_ranks):
 
 
 # ---- 1/8 shards of the bench sizes: the b-split grid (2-4 CTAs per work item) --------------------
-@pytest.mark.parametrize("n,rank", [(256, 5), (128, 7), (64, 0)])
-def test_eighth_shard_with_b_splits_known_answers(n, rank):
-    """What one GPU of eight runs at n_bf=256 / 128: so few equal-size work items that each is
-    split along b (csrc/jk_full.cu scfb_full_b_splits), J becomes a per-CTA partial too and the
-    persistent kernel's queue hands out chunk x slab x split items.  Unit densities pin the
-    owned columns bit for bit (UHF, so both K accumulators are exercised)."""
+@pytest.mark.parametrize("n,rank,split,tma", [(256, 5, None, "1"), (256, 5, "2", "1"), (128, 7, "4", "1"),
+                                              (64, 0, "2", "1"), (128, 3, None, "0"), (64, 1, "2", "0")])
+def test_eighth_shard_with_b_splits_known_answers(n, rank, split, tma, monkeypatch):
+    """What one GPU of eight runs at n_bf=256 / 128, with the work items split along b
+    (csrc/jk_full.cu scfb_full_b_splits: the LDG kernel's rule, forced for the TMA kernel): J
+    becomes a per-CTA partial too and the persistent kernel's queue hands out chunk x slab x split
+    items.  Unit densities pin the owned columns bit for bit (UHF: both K accumulators)."""
+    monkeypatch.setenv("SCFB_FULL_TMA", tma)           # both read when the handle is created / launched
+    if split:
+        monkeypatch.setenv("SCFB_FULL_BSPLIT", split)
     b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, rank=rank, n_ranks=8)
     lo, hi = b.shard_range
     assert hi - lo == n // 8
