@@ -592,8 +592,17 @@ __global__ void k_reduce_kernel(const double* __restrict__ kpart, const double* 
     const int slab = (int)(rest % n_slabs);
     const int s = (int)(rest / n_slabs);
     const double* p = kpart + (((size_t)slab * parts) * n_spin + s) * n + a;
+    const size_t stride = (size_t)n_spin * n;
     double v = 0.0;
-    for (size_t c = 0; c < parts; ++c) v += p[c * n_spin * n];
+    size_t c = 0;
+    for (; c + 8 <= parts; c += 8) {  // eight loads in flight, added in the same fixed order
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __ldg(p + (c + u) * stride);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v += t[u];
+    }
+    for (; c < parts; ++c) v += __ldg(p + c * stride);
     jk[(size_t)(1 + s) * n * n + (size_t)(nu_lo + slab) * n + a] = v;
     if (bs > 1 && s == 0) {  // this thread also owns J[c = a, nu]
       const double* q = jpart + (((size_t)slab * n_chunks + a / TC) * bs) * TC + a % TC;
