@@ -440,6 +440,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -461,35 +464,64 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // ------------------------------------------------------------------------------------------
-// v4 (SCFB_PACKED_TMA=1, measured slower: profiles/README.md): the one-warp work item of `packed_item`, with every per-row operand delivered by the TMA
-// engine instead of per-lane LDGSTS.  ncu on v2 shows the LSU data pipe at 66 % with two warps per
-// scheduler: each row costs ~160 LSU cycles per warp, 80 of them the LDGSTS writes of the ERI pairs
-// and of the density row.  Here lane 0 posts, three rows ahead, one 1-D bulk copy (cp.async.bulk ->
-// SASS UBLKCP) per k-segment (<= 512 B: this warp's 64 l values), one per spin for D[j, wl..wl+63]
-// and one per spin for D[j, k0..k0+KC), all completing on the stage's mbarrier; the warp that
-// issued them is also their only consumer, so there is no "empty" barrier, no second warp and no
-// CTA-level synchronisation.  2 Dtot[(i,j)] (8 bytes, not bulk-copyable) is an ordinary load issued
-// one row early.  Requires n even (16-byte alignment of the density rows).
+// v5 (SCFB_PACKED_TMA=1): the one-warp work item of `packed_item`, fed by the TMA engine from a
+// DIFFERENT warp.  ncu on v2 shows the LSU data pipe at 66 % with two warps per scheduler: per
+// row and warp ~160 LSU cycles, 80 of them the LDGSTS writes of the ERI pairs and of the density
+// row.  v4 let lane 0 of the consuming warp post bulk copies instead (cp.async.bulk, SASS UBLKCP)
+// and lost: a bulk copy costs its issuer ~35 instructions / ~70 cycles
+// (benchmarks/micro/bulk_copy_rate.cu), ten of them per row came out of the consumer's own row
+// budget (7.0 vs 5.5 ms).  Here a CTA is WS_PAIRS independent (producer warp, consumer warp)
+// pairs: the producer draws work items from a global counter (heaviest i first), publishes them
+// to its consumer through a two-deep queue and posts, up to DEPTH rows ahead, one bulk copy per
+// k-segment (<= 512 B: the consumer's 64 l values), one per spin for D[j, wl..wl+63] and one per
+// spin for D[j, k0..k0+KC), all completing on the stage's "full" mbarrier; the consumer reads its
+// operands out of the stage, hands it back ("empty" mbarrier) and does the math of `packed_item`.
+// Pairs never synchronise with each other; the ring runs on across items.  setmaxnreg moves
+// registers from the producer warpgroups to the consumer warpgroups.  Requires n even.
 // ------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int bulk_stage_doubles(int nspin, int kc) {
+constexpr int WS_PAIRS = 8;
+constexpr int WS_PRODUCER_REGS = 48, WS_CONSUMER_REGS = 208;  // 256 * (48 + 208) = 65536
+__host__ __device__ constexpr int ws_stage_doubles(int nspin, int kc) {
   return kc * 64 + nspin * 64 + nspin * kc;
 }
-__host__ __device__ constexpr size_t bulk_smem_bytes(int nspin, int kc) {
-  return (size_t)packed_rb(nspin, kc) * (nspin * kc + 1) * YS * sizeof(double)
-         + (size_t)DEPTH * bulk_stage_doubles(nspin, kc) * sizeof(double) + DEPTH * sizeof(uint64_t);
+__host__ __device__ constexpr int ws_pair_doubles(int nspin, int kc) {
+  return packed_rb(nspin, kc) * (nspin * kc + 1) * YS + DEPTH * ws_stage_doubles(nspin, kc);
 }
 
+struct WsItem {
+  int i, k0, wl;
+  uint32_t rot;
+  bool valid;
+};
+// linear index -> item, heaviest rows first; kc fastest so that neighbours share D rows in L2
+template <int KC>
+__device__ __forceinline__ WsItem ws_decode(int idx, int n, int i_hi) {
+  const int nk = (n + KC - 1) / KC, nl = (n + 63) / 64;
+  const int per_i = nk * nl;
+  WsItem it;
+  it.i = i_hi - 1 - idx / per_i;
+  const int r = idx % per_i;
+  const int kc = r % nk, lw = r / nk;
+  it.k0 = kc * KC;
+  it.wl = lw * 64;
+  it.rot = (uint32_t)kc * 40503u + (uint32_t)lw * 9973u + (uint32_t)it.i * 17u;
+  it.valid = it.k0 <= it.i && it.wl <= min(it.k0 + KC - 1, it.i);
+  return it;
+}
+
+// consumer side of one work item; `sc` is the pair's running stage counter
 template <int NSPIN, int KC, int MODE>
-__device__ __forceinline__ void packed_item_bulk(const double* __restrict__ eri_i,
-                                                 const double* __restrict__ D, size_t dstride,
-                                                 const double* __restrict__ dq2,
-                                                 double* __restrict__ Kp, double* __restrict__ Jp,
-                                                 double* __restrict__ ys, double* __restrict__ stages,
-                                                 uint64_t* __restrict__ bars, int n, int i, int k0,
-                                                 int wl, int lane, uint32_t rot) {
+__device__ __forceinline__ void ws_consume_item(const double* __restrict__ D, size_t dstride,
+                                                const double* __restrict__ dq2,
+                                                double* __restrict__ Kp, double* __restrict__ Jp,
+                                                double* __restrict__ ys,
+                                                const double* __restrict__ stages,
+                                                uint64_t* __restrict__ full, uint64_t* __restrict__ empty,
+                                                int n, int i, int k0, int wl, int lane, uint32_t rot,
+                                                uint32_t& sc) {
   constexpr int NV = NSPIN * KC + 1;
   constexpr int RB = packed_rb(NSPIN, KC);
-  constexpr int STG = bulk_stage_doubles(NSPIN, KC);
+  constexpr int STG = ws_stage_doubles(NSPIN, KC);
   const int l0 = wl + 2 * lane;
   const int kmax = min(k0 + KC - 1, i);
   const bool l0_in = MODE == 0 || l0 <= kmax, l1_in = MODE == 0 || l0 + 1 <= kmax;
@@ -502,7 +534,7 @@ __device__ __forceinline__ void packed_item_bulk(const double* __restrict__ eri_
   for (int s = 0; s < NSPIN; ++s) {
     const double* di = D + s * dstride + (size_t)i * n;
     di_l[s][0] = __ldg(di + lc);
-    di_l[s][1] = __ldg(di + lc + 1);
+    di_l[s][1] = __ldg(di + lc + 1);  // beyond-the-edge values only ever meet zero ERI entries
   }
 #pragma unroll
   for (int t = 0; t < KC; ++t) {
@@ -527,48 +559,7 @@ __device__ __forceinline__ void packed_item_bulk(const double* __restrict__ eri_
   for (int s = 0; s < NSPIN; ++s) a2[s][0] = a2[s][1] = 0.0;
 
   const int rows = i + 1;
-  if (lane == 0) {
-#pragma unroll
-    for (int d = 0; d < DEPTH; ++d) mbar_init(bars + d, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-
-  // lane 0 only: post the copies of row (i,j) into `stage`
-  auto issue_row = [&](int stage, const double* row, int j) {
-    double* dst = stages + stage * STG;
-    uint64_t* bar = bars + stage;
-    uint32_t len[KC], total = NSPIN * (64 + KC);
-#pragma unroll
-    for (int t = 0; t < KC; ++t) {
-      const int k = k0 + t;
-      if (MODE == 0) {
-        len[t] = 64;
-      } else {
-        // stored (padded) length of segment k of row (i,j), clipped to this warp's l window
-        int seg = k > i ? 0 : ((k < i ? k : j) + 2) & ~1;
-        seg -= wl;
-        len[t] = seg <= 0 ? 0u : (uint32_t)(seg < 64 ? seg : 64);
-      }
-      total += len[t];
-    }
-    mbar_expect_tx(bar, total * 8u);
-#pragma unroll
-    for (int t = 0; t < KC; ++t)
-      if (MODE == 0 || len[t])
-        bulk_g2s(dst + t * 64, row + seg_off(min(k0 + t, i)) + wl, len[t] * 8u, bar);
-#pragma unroll
-    for (int s = 0; s < NSPIN; ++s) {
-      const double* dj = D + s * dstride + (size_t)j * n;
-      bulk_g2s(dst + KC * 64 + s * 64, dj + wl, 512u, bar);
-      bulk_g2s(dst + KC * 64 + NSPIN * 64 + s * KC, dj + k0, KC * 8u, bar);
-    }
-  };
-
-  const int j_first = (int)(rot % (uint32_t)rows);
-  int j = j_first;  // load side
-  const double* row = eri_i + (uint64_t)j * Ei + seg_off(j);
-  int jc = j_first;  // consume side
+  int jc = (int)(rot % (uint32_t)rows);  // same rotated row order as the producer
   double* kj0 = Kp + (size_t)jc * n;
   int parked = 0, j_tile = jc;
   double dp2 = __ldg(dq2 + Ei + jc);
@@ -589,44 +580,21 @@ __device__ __forceinline__ void packed_item_bulk(const double* __restrict__ eri_
       int jr = j_tile + red_r;
       if (jr >= rows) jr -= rows;
       if (red_v == NV - 1) {
-        atomicAdd(Jp + Ei + jr, tot);
+        atomicAdd(Jp + Ei + jr, tot);  // J~[pr(i,j)]
       } else {
         const int sp = red_v / KC, t = red_v - sp * KC;
-        if (MODE == 0 || k0 + t <= i) atomicAdd(Kp + sp * dstride + (size_t)jr * n + k0 + t, tot);
+        if (MODE == 0 || k0 + t <= i) atomicAdd(Kp + sp * dstride + (size_t)jr * n + k0 + t, tot);  // K'[j,k]
       }
     }
     __syncwarp();
   };
 
-  auto advance = [&]() {
-    if (j + 1 == rows) {
-      j = 0;
-      row = eri_i;
-    } else {
-      row += Ei + ((j + 2) & ~1);
-      ++j;
-    }
-  };
-
-  if (lane == 0) {
-#pragma unroll
-    for (int d = 0; d < DEPTH - 1; ++d)
-      if (d < rows) {
-        issue_row(d, row, j);
-        advance();
-      }
-  }
   for (int step = 0; step < rows; ++step) {
-    __syncwarp();  // every lane has finished reading the stage that is refilled next
-    if (lane == 0 && step + DEPTH - 1 < rows) {
-      issue_row((step + DEPTH - 1) % DEPTH, row, j);
-      advance();
-    }
     const int jn = jc + 1 == rows ? 0 : jc + 1;
     const double dp2_next = __ldg(dq2 + Ei + jn);
-    const int stage = step % DEPTH;
-    mbar_wait(bars + stage, (step / DEPTH) & 1);
-    const double* st = stages + stage * STG;
+    const uint32_t slot = sc % DEPTH;
+    mbar_wait(full + slot, (sc / DEPTH) & 1);
+    const double* st = stages + slot * STG;
     double2 w[KC];
 #pragma unroll
     for (int t = 0; t < KC; ++t) {
@@ -649,6 +617,10 @@ __device__ __forceinline__ void packed_item_bulk(const double* __restrict__ eri_
         dj_k[s][t + 1] = u.y;
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + slot);  // operands are in registers: hand the stage back
+    ++sc;
+
     double jp0 = 0.0, jp1 = 0.0;
     double z[NSPIN][2];
 #pragma unroll
@@ -708,33 +680,142 @@ __device__ __forceinline__ void packed_item_bulk(const double* __restrict__ eri_
     }
 }
 
-// grid = (n_kchunks, n_i_owned, n_lblocks of 64), block = one warp.
-template <int NSPIN, int KC, int MINB>
-__global__ void __launch_bounds__(32, MINB)
-jk_packed_bulk_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Btab,
-                      uint64_t shard_offset, const double* __restrict__ D, size_t dstride,
-                      const double* __restrict__ dq2, double* __restrict__ Kp,
-                      double* __restrict__ Jp, int n, int i_lo) {
-  extern __shared__ __align__(128) unsigned char bk_smem[];
+// grid = one CTA per SM; block = 2 * WS_PAIRS warps (consumers first); dynamic smem = per-pair
+// [row-sum tile | DEPTH stages].
+template <int NSPIN, int KC>
+__global__ void __launch_bounds__(64 * WS_PAIRS, 1)
+jk_packed_ws_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Btab,
+                    uint64_t shard_offset, const double* __restrict__ D, size_t dstride,
+                    const double* __restrict__ dq2, double* __restrict__ Kp,
+                    double* __restrict__ Jp, int n, int i_lo, int i_hi, int* __restrict__ sched) {
+  extern __shared__ __align__(128) double ws_smem[];
+  __shared__ uint64_t full[WS_PAIRS][DEPTH], empty[WS_PAIRS][DEPTH];
+  __shared__ uint64_t item_full[WS_PAIRS][2], item_empty[WS_PAIRS][2];
+  __shared__ int item_q[WS_PAIRS][2];
   constexpr int TILE = packed_rb(NSPIN, KC) * (NSPIN * KC + 1) * YS;
-  double* ys = reinterpret_cast<double*>(bk_smem);
+  constexpr int STG = ws_stage_doubles(NSPIN, KC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool producer = warp >= WS_PAIRS;
+  const int p = producer ? warp - WS_PAIRS : warp;
+  double* ys = ws_smem + (size_t)p * ws_pair_doubles(NSPIN, KC);
   double* stages = ys + TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + DEPTH * bulk_stage_doubles(NSPIN, KC));
-  const int i = i_lo + blockIdx.y;
-  const int k0 = blockIdx.x * KC;
-  if (k0 > i) return;
-  const int wl = blockIdx.z * 64;
-  const int kmax = min(k0 + KC - 1, i);
-  if (wl > kmax) return;
-  const int lane = threadIdx.x;
-  const double* eri_i = eri + (Btab[i] - shard_offset);
-  const uint32_t rot = blockIdx.x * 40503u + blockIdx.z * 9973u + blockIdx.y * 17u;
-  if (kmax == i)
-    packed_item_bulk<NSPIN, KC, 2>(eri_i, D, dstride, dq2, Kp, Jp, ys, stages, bars, n, i, k0, wl, lane, rot);
-  else if (wl + 63 <= k0)
-    packed_item_bulk<NSPIN, KC, 0>(eri_i, D, dstride, dq2, Kp, Jp, ys, stages, bars, n, i, k0, wl, lane, rot);
-  else
-    packed_item_bulk<NSPIN, KC, 1>(eri_i, D, dstride, dq2, Kp, Jp, ys, stages, bars, n, i, k0, wl, lane, rot);
+  const int per_i = ((n + KC - 1) / KC) * ((n + 63) / 64);
+  const int total = (i_hi - i_lo) * per_i;
+
+  if (threadIdx.x < WS_PAIRS) {
+    for (int d = 0; d < DEPTH; ++d) {
+      mbar_init(&full[threadIdx.x][d], 1);
+      mbar_init(&empty[threadIdx.x][d], 1);
+    }
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(&item_full[threadIdx.x][q], 1);
+      mbar_init(&item_empty[threadIdx.x][q], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (producer) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_PRODUCER_REGS));
+    // All 32 lanes stay converged and each owns at most ONE copy job of a row (lane t < KC: the
+    // k-segment k0+t; then per spin the D[j, l-window] piece and the D[j, k-chunk] piece): the
+    // address/length arithmetic runs once, SIMT-parallel, and only the UBLKCP issue itself is
+    // serialised over the active lanes (~8 instructions each) — a single posting lane needed
+    // ~450 instructions per row and was the bottleneck (6.25 ms).
+    static_assert(KC + 2 * NSPIN <= 32, "one copy job per producer lane");
+    uint32_t sc = 0;
+    for (int k = 0;; ++k) {
+      // draw the next valid item (lane 0 draws, everybody decodes)
+      int idx;
+      WsItem it;
+      it.valid = false;
+      do {
+        idx = lane == 0 ? atomicAdd(sched, 1) : 0;
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx < total) it = ws_decode<KC>(idx, n, i_hi);
+      } while (idx < total && !it.valid);
+      if (idx >= total) idx = -1;
+      if (lane == 0) {
+        if (k >= 2) mbar_wait(&item_empty[p][k & 1], ((k >> 1) & 1) ^ 1);
+        item_q[p][k & 1] = idx;
+        mbar_arrive(&item_full[p][k & 1]);  // release: the store above is visible to the waiter
+      }
+      __syncwarp();
+      if (idx < 0) break;
+
+      const int i = it.i, k0 = it.k0, wl = it.wl;
+      const int rows = i + 1;
+      const uint64_t Ei = seg_off(i);
+      const double* eri_i = eri + (Btab[i] - shard_offset);
+      const bool interior = k0 + KC - 1 < i && wl + 63 <= k0;  // MODE 0: every ERI copy is 512 bytes
+      int j = (int)(it.rot % (uint32_t)rows);
+      const double* row = eri_i + (uint64_t)j * Ei + seg_off(j);
+      // this lane's job: ERI segment (lane < KC) or a density piece
+      const int kk = k0 + lane;                       // segment index if lane < KC
+      const int q = lane - KC, sp = q >> 1;           // density job if 0 <= q < 2*NSPIN
+      const bool seg_job = lane < KC, dl_job = q >= 0 && q < 2 * NSPIN && !(q & 1),
+                 dk_job = q >= 0 && q < 2 * NSPIN && (q & 1);
+      const uint32_t soff = seg_job ? (uint32_t)seg_off(min(kk, i)) + (uint32_t)wl : 0u;
+      const int my_dst = seg_job ? lane * 64 : (dl_job ? KC * 64 + sp * 64 : KC * 64 + NSPIN * 64 + sp * KC);
+      const double* dsrc = D + (dl_job || dk_job ? sp * dstride : 0) + (dl_job ? wl : k0);  // + j*n per row
+      for (int step = 0; step < rows; ++step) {
+        const uint32_t slot = sc % DEPTH;
+        mbar_wait(&empty[p][slot], ((sc / DEPTH) & 1) ^ 1);
+        double* dst = stages + slot * STG + my_dst;
+        uint64_t* bar = &full[p][slot];
+        uint32_t bytes = 0;
+        const double* src = row + soff;
+        if (seg_job) {
+          uint32_t len = 64;
+          if (!interior) {
+            // stored (padded) length of segment kk of row (i,j), clipped to this warp's l window
+            int seg = kk > i ? 0 : ((kk < i ? kk : j) + 2) & ~1;
+            seg -= wl;
+            len = seg <= 0 ? 0u : (uint32_t)(seg < 64 ? seg : 64);
+          }
+          bytes = len * 8u;
+        } else if (dl_job || dk_job) {
+          src = dsrc + (size_t)j * n;
+          bytes = dl_job ? 512u : KC * 8u;
+        }
+        if (bytes) bulk_g2s(dst, src, bytes, bar);
+        const uint32_t all = __reduce_add_sync(0xffffffffu, bytes);
+        // the one arrival of the phase; copies that landed earlier are already accounted for
+        if (lane == 0) mbar_expect_tx(bar, all);
+        ++sc;
+        if (j + 1 == rows) {
+          j = 0;
+          row = eri_i;
+        } else {
+          row += Ei + ((j + 2) & ~1);
+          ++j;
+        }
+      }
+    }
+    return;
+  }
+
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_CONSUMER_REGS));
+  uint32_t sc = 0;
+  for (int k = 0;; ++k) {
+    mbar_wait(&item_full[p][k & 1], (k >> 1) & 1);
+    const int idx = item_q[p][k & 1];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&item_empty[p][k & 1]);
+    if (idx < 0) break;
+    const WsItem it = ws_decode<KC>(idx, n, i_hi);
+    const int kmax = min(it.k0 + KC - 1, it.i);
+    if (kmax == it.i)
+      ws_consume_item<NSPIN, KC, 2>(D, dstride, dq2, Kp, Jp, ys, stages, full[p], empty[p], n, it.i, it.k0,
+                                    it.wl, lane, it.rot, sc);
+    else if (it.wl + 63 <= it.k0)
+      ws_consume_item<NSPIN, KC, 0>(D, dstride, dq2, Kp, Jp, ys, stages, full[p], empty[p], n, it.i, it.k0,
+                                    it.wl, lane, it.rot, sc);
+    else
+      ws_consume_item<NSPIN, KC, 1>(D, dstride, dq2, Kp, Jp, ys, stages, full[p], empty[p], n, it.i, it.k0,
+                                    it.wl, lane, it.rot, sc);
+  }
 }
 
 // dq2[seg_off(k) + l] = 2 * Dtot[k,l] for l <= k, pads = 0;  dpad = D with DPAD zeros appended
@@ -881,7 +962,7 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
   if (n_i > 0) {
     double* Jp = h->pk_acc;
     double* Kp = h->pk_acc + PQ;
-    static const int use_tma = [] {  // SCFB_PACKED_TMA=1 selects the bulk-copy (v4) kernel
+    static const int use_tma = [] {  // SCFB_PACKED_TMA=1 selects the warp-specialised bulk-copy (v5) kernel (RHF)
       const char* v = std::getenv("SCFB_PACKED_TMA");
       return v ? std::atoi(v) : 0;
     }();
@@ -894,24 +975,24 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
       return v ? std::atoi(v) : 0;
     }();
     const int kc = kc_sel == 4 || kc_sel == 8 ? kc_sel : 8;
-    if (use_tma && n % 2 == 0) {
-      dim3 bgrid((n + kc - 1) / kc, n_i, (n + 63) / 64);
-#define SCFB_PK_BULK(NS, KCV, MINB)                                                              \
-  do {                                                                                           \
-    const size_t sm_ = bulk_smem_bytes(NS, KCV);                                                 \
-    cudaFuncSetAttribute(jk_packed_bulk_kernel<NS, KCV, MINB>,                                   \
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_);                 \
-    jk_packed_bulk_kernel<NS, KCV, MINB><<<bgrid, 32, sm_, h->stream>>>(                         \
-        h->eri, h->pk_btab, h->pk_offset, h->pk_dpad, dstride, h->pk_dq2, Kp, Jp, n, h->i_lo);   \
-  } while (0)
-      if (n_spin == 1 && kc == 8) SCFB_PK_BULK(1, 8, 8);
-      else if (n_spin == 1) SCFB_PK_BULK(1, 4, 12);
-      else if (kc == 8) SCFB_PK_BULK(2, 8, 8);
-      else SCFB_PK_BULK(2, 4, 8);
-#undef SCFB_PK_BULK
+    if (use_tma && n % 2 == 0 && n_spin == 1 && kc == 8) {
+      static int n_sm = 0;
+      if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+      }
+      const size_t sm_ = (size_t)WS_PAIRS * ws_pair_doubles(1, 8) * sizeof(double);
+      cudaFuncSetAttribute(jk_packed_ws_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_);
+      e = cudaMemsetAsync(h->sched, 0, sizeof(int), h->stream);
+      if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+      jk_packed_ws_kernel<1, 8><<<n_sm, 64 * WS_PAIRS, sm_, h->stream>>>(
+          h->eri, h->pk_btab, h->pk_offset, h->pk_dpad, dstride, h->pk_dq2, Kp, Jp, n, h->i_lo, h->i_hi,
+          h->sched);
       e = cudaGetLastError();
       if (e != cudaSuccess)
-        return scfb_fail(h, SCFB_ERR_CUDA, "jk_packed_bulk_kernel launch: %s", cudaGetErrorString(e));
+        return scfb_fail(h, SCFB_ERR_CUDA, "jk_packed_ws_kernel launch: %s", cudaGetErrorString(e));
       h->launches += 1;
       if (h->timed) cudaEventRecord(h->ev[1], h->stream);
       unpack_jk_kernel<<<148 * 2, 256, 0, h->stream>>>(h->pk_acc, h->pk_acc + PQ, h->jk, n, n_spin);
