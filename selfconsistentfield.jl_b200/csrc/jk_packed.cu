@@ -962,10 +962,10 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
   if (n_i > 0) {
     double* Jp = h->pk_acc;
     double* Kp = h->pk_acc + PQ;
-    static const int use_tma = [] {  // SCFB_PACKED_TMA=1 selects the warp-specialised bulk-copy (v5) kernel (RHF)
-      const char* v = std::getenv("SCFB_PACKED_TMA");
-      return v ? std::atoi(v) : 0;
-    }();
+    // SCFB_PACKED_TMA=1 selects the warp-specialised bulk-copy (v5) kernel (RHF, even n); read per
+    // launch so that one test process can cover both kernels
+    const char* tma_env = std::getenv("SCFB_PACKED_TMA");
+    const int use_tma = tma_env ? std::atoi(tma_env) : 0;
     static const int minb_sel = [] {  // tuning knob: SCFB_PACKED_MINB=3|4 (CTAs per SM, KC=4 RHF)
       const char* v = std::getenv("SCFB_PACKED_MINB");
       return v ? std::atoi(v) : 4;
