@@ -93,7 +93,8 @@ int scfb_eri_download(scfb_handle_t h, double* host_shard);
  * returns the full result. */
 int scfb_fock_jk(scfb_handle_t h, int n_spin, const double* density,
                  const double* total_density, double* out);
-/* Same with DEVICE pointers, asynchronous on the handle's stream. */
+/* Same with DEVICE pointers, asynchronous on the handle's stream.  d_density and
+ * d_total_density must be 16-byte aligned (SCFB_ERR_ARG otherwise). */
 int scfb_fock_jk_dev(scfb_handle_t h, int n_spin, const double* d_density,
                      const double* d_total_density, double* d_out);
 /* J (n*n) and K (n*n*n_spin) separately, overwritten, host pointers. */

@@ -302,6 +302,10 @@ int scfb_fock_jk_dev(scfb_handle_t h, int n_spin, const double* d_density,
                      const double* d_total_density, double* d_out) {
   if (int rc = check_handle(h)) return rc;
   if (int rc = check_build_args(h, n_spin, d_density, d_total_density, d_out)) return rc;
+  // the kernels read the densities with 128-bit loads / 16-byte-granular bulk copies: a misaligned
+  // pointer would fault on the device (a sticky error), so it is refused here
+  SCFB_REQUIRE(h, ((uintptr_t)d_density | (uintptr_t)d_total_density) % 16 == 0,
+               "device density pointers must be 16-byte aligned");
   if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
   if (int rc = launch_jk(h, n_spin, d_density, d_total_density)) return rc;
   if (h->n_ranks > 1 && scfb_peer_ready(h)) {
