@@ -639,15 +639,14 @@ cudaError_t launch_tma(scfb_handle_s* h, const double* d_density, const double* 
   if (S > TMA_MAX_STAGES) S = TMA_MAX_STAGES;
   if (S < 2) S = 2;
   const size_t smem = (size_t)S * stage;
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[NSPIN]) {
+  if (!h->tma_attr[NSPIN]) {  // function attributes are per device, hence per handle
     cudaError_t e = cudaFuncSetAttribute(jk_full_tma_kernel<NSPIN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     if (e == cudaSuccess)  // two CTAs only fit with the largest shared-memory carveout
       e = cudaFuncSetAttribute(jk_full_tma_kernel<NSPIN>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    attr_set[NSPIN] = true;
+    h->tma_attr[NSPIN] = true;
   }
   static const bool verbose = std::getenv("SCFB_VERBOSE") != nullptr;
   if (verbose) {
@@ -658,13 +657,11 @@ cudaError_t launch_tma(scfb_handle_s* h, const double* d_density, const double* 
             "(%d without dynamic smem)\n", NSPIN, n, R, G, S, smem, MAX_THREADS + 32 * TMA_PRODUCERS, occ, occ0);
   }
   const long items = (long)n_chunks * n_slabs * h->b_splits;
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
+  if (h->n_sm == 0) {
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
+    if (h->n_sm <= 0) h->n_sm = 148;
   }
+  const int n_sm = h->n_sm;
   static const int per_sm = [] {  // SCFB_FULL_TMA_CTAS=0: one CTA per item (non-persistent), else CTAs per SM
     const char* v = std::getenv("SCFB_FULL_TMA_CTAS");
     return v ? std::atoi(v) : 2;

@@ -976,13 +976,11 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
     }();
     const int kc = kc_sel == 4 || kc_sel == 8 ? kc_sel : 8;
     if (use_tma && n % 2 == 0 && n_spin == 1 && kc == 8) {
-      static int n_sm = 0;
-      if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
+      if (h->n_sm == 0) {
+        cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
+        if (h->n_sm <= 0) h->n_sm = 148;
       }
+      const int n_sm = h->n_sm;
       const size_t sm_ = (size_t)WS_PAIRS * ws_pair_doubles(1, 8) * sizeof(double);
       cudaFuncSetAttribute(jk_packed_ws_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_);
       e = cudaMemsetAsync(h->sched, 0, sizeof(int), h->stream);

@@ -38,7 +38,9 @@ struct scfb_handle_s {
   double* jk_sum = nullptr;     // allreduce result (n_ranks > 1); == jk when single rank
   double* kpart = nullptr;      // per-(nu, c-chunk, b-split) partial K rows
   double* jpart = nullptr;      // per-(nu, c-chunk, b-split) partial J values (b_splits > 1)
-  int* sched = nullptr;         // work-item counter of the persistent full-layout kernel
+  int* sched = nullptr;         // work-item counter of the persistent kernels
+  int n_sm = 0;                 // SM count of this handle's device (lazily queried)
+  bool tma_attr[3] = {false, false, false};  // per NSPIN: smem attributes of jk_full_tma_kernel set on this device
   int b_splits = 1;             // CTAs sharing one (nu, c-chunk) work item along b
   uint64_t kpart_elems = 0;
   double* h_stage = nullptr;    // pinned host staging, 5*n*n
