@@ -3,14 +3,15 @@
     /root/reference/examples/HartreeFock.jl  +  examples/print_results.jl
 with the Fock build running on the B200 through libscf_b200.so.
 
-    python examples/HartreeFock.py [--unrestricted|--restricted] <integral_file> [<outfile.npz>]
+    python examples/HartreeFock.py [--unrestricted|--restricted] <integral_file> [<outfile>]
 
 <integral_file> is an integral dump in the reference's HDF5 schema
 (scripts/dump_integrals_pyscf.py:21-51, e.g. test/data/integrals_be_3-21g.hdf5) or one of the
 converted fixtures under tests/golden/*.npz.  Same flow as `hartree_fock` (HartreeFock.jl:100-134):
 load -> assemble_hf_problem -> hcore guess (-> break_spin_symmetry) -> run_scf with
 max_error_norm=5e-7, max_energy_total_change=1.25e-7 -> termwise energies -> print.
-The result dump is a NumPy .npz (the reference writes a molsturm HDF5 file; out of scope).
+<outfile> is written in the molsturm HDF5 layout like the reference does
+(src/util/dump_molsturm_hdf5.jl; selfconsistentfield.jl_b200/dump.py), or as a NumPy archive if it ends in .npz.
 """
 import os
 import sys
@@ -118,8 +119,11 @@ def hartree_fock(intfile, restricted=None, ofile=None):
     S.compute_termwise_hf_energies(res, problem)
     print_results(problem, res)
     if ofile is not None:
-        np.savez(ofile, orben=res["orben"], orbcoeff=res["orbcoeff"], density=res["density"],
-                 fock=res["fock"], **{f"energy_{k}": v for k, v in res["energies"].items()})
+        if ofile.endswith(".npz"):
+            np.savez(ofile, orben=res["orben"], orbcoeff=res["orbcoeff"], density=res["density"],
+                     fock=res["fock"], **{f"energy_{k}": v for k, v in res["energies"].items()})
+        else:                                          # HartreeFock.jl:131-133
+            scf_b200.dump_molsturm_hdf5(integrals, res, ofile)
     return res
 
 

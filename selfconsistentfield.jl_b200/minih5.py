@@ -1,4 +1,4 @@
-"""Minimal read-only HDF5 parser (struct + zlib only).
+"""Minimal HDF5 reader, plus an even smaller writer (struct + zlib only).
 
 Host-side mirror of the *reading* half of the reference's integral loader
 (`/root/reference/src/util/load_integral_hdf5.jl:6-55` goes through HDF5.jl,
@@ -11,6 +11,11 @@ superblock v0, v1 object headers (with continuation blocks), old-style groups
 chunked (v1 B-tree, deflate filter, optional shuffle) layout, little-endian
 fixed-point / IEEE float scalars, and variable-length strings in the global
 heap (`GCOL`).  Anything else raises `H5FormatError` — never a silent guess.
+
+`write_h5` produces the same dialect (superblock v0, v1 object headers, one old-style
+root group, contiguous little-endian datasets, fixed-length string attributes): what the
+result dump (`dump.py`, reference `src/util/dump_molsturm_hdf5.jl`) needs.  It is verified
+against this module's reader only — no libhdf5 exists here to cross-check it.
 
 Datasets are returned as C-ordered numpy arrays with the on-disk (C-order)
 dimensions.  HDF5.jl hands Julia the same bytes with the dimensions reversed;
@@ -137,6 +142,41 @@ class MiniH5:
     def keys(self, path="/"):
         kids = self._children(self._lookup(path))
         return sorted(kids) if kids else []
+
+    def attrs(self, path="/"):
+        """Attributes of a group or dataset: fixed-length strings and numeric scalars/arrays
+        (v1 attribute messages; variable-length strings are resolved through the global heap)."""
+        out = {}
+        for mtype, _, p in self._messages(self._lookup(path)["ohdr"] + self.base):
+            if mtype != 0x000C:
+                continue
+            ver, _, nlen, tlen, slen = struct.unpack_from("<BBHHH", p, 0)
+            if ver != 1:
+                raise H5FormatError(f"attribute message version {ver} unsupported (only v1)")
+            pad = lambda x: (x + 7) // 8 * 8
+            pos = 8
+            name = p[pos:pos + nlen].split(b"\0")[0].decode("utf-8")
+            pos += pad(nlen)
+            tmsg = p[pos:pos + tlen]
+            pos += pad(tlen)
+            smsg = p[pos:pos + slen]
+            pos += pad(slen)
+            rank = smsg[1]
+            dims = struct.unpack_from(f"<{rank}Q", smsg, 8 if smsg[0] == 1 else 4) if rank else ()
+            count = int(np.prod(dims)) if dims else 1
+            cls, size = tmsg[0] & 0x0F, struct.unpack_from("<I", tmsg, 4)[0]
+            raw = p[pos:pos + count * size]
+            if cls == 3:      # fixed-length string
+                vals = [raw[i * size:(i + 1) * size].split(b"\0")[0].decode("utf-8") for i in range(count)]
+                out[name] = vals[0] if dims == () else vals
+            elif cls == 9:
+                vals = [self._vlen_string(bytes(raw[16 * i:16 * i + 16])) for i in range(count)]
+                out[name] = vals[0] if dims == () else vals
+            else:
+                _kind, np_dtype, _ = self._datatype(tmsg)
+                arr = np.frombuffer(raw, dtype=np_dtype, count=count)
+                out[name] = arr[0] if dims == () else arr.reshape(dims).copy()
+        return out
 
     # ---- datasets ---------------------------------------------------------
     def read(self, path):
@@ -328,3 +368,128 @@ class MiniH5:
                 return b[pos + 16: pos + 16 + length].decode("utf-8")
             pos += 16 + ((osize + 7) // 8) * 8
         raise H5FormatError("global heap object not found")
+
+
+# ---- writer ---------------------------------------------------------------------------------
+def _pad8(b: bytes) -> bytes:
+    return b + b"\0" * (-len(b) % 8)
+
+
+def _dtype_message(dt: np.dtype) -> bytes:
+    """Datatype message (version 1) for little-endian ints, floats and fixed-length strings."""
+    if dt.kind == "f" and dt.itemsize in (4, 8):
+        exp_bits, man_bits = (8, 23) if dt.itemsize == 4 else (11, 52)
+        bias = (1 << (exp_bits - 1)) - 1
+        head = struct.pack("<BBBBI", 0x11, 0x20, dt.itemsize * 8 - 1, 0, dt.itemsize)
+        return head + struct.pack("<HHBBBBI", 0, dt.itemsize * 8, man_bits, exp_bits, 0, man_bits, bias)
+    if dt.kind in "iu" or dt.kind == "b":
+        signed = 0x08 if dt.kind == "i" else 0x00
+        return struct.pack("<BBBBI", 0x10, signed, 0, 0, dt.itemsize) + struct.pack("<HH", 0, dt.itemsize * 8)
+    if dt.kind == "S":
+        return struct.pack("<BBBBI", 0x13, 0x00, 0, 0, dt.itemsize)     # null-terminated ASCII
+    raise H5FormatError(f"cannot write dtype {dt}")
+
+
+def _dataspace_message(shape) -> bytes:
+    return struct.pack("<BBBBI", 1, len(shape), 0, 0, 0) + b"".join(struct.pack("<Q", d) for d in shape)
+
+
+def _message(mtype: int, payload: bytes) -> bytes:
+    payload = _pad8(payload)
+    return struct.pack("<HHBBBB", mtype, len(payload), 0, 0, 0, 0) + payload
+
+
+def _object_header(messages) -> bytes:
+    body = b"".join(messages)
+    return struct.pack("<BBHII", 1, 0, len(messages), 1, len(body)) + b"\0" * 4 + body
+
+
+def _as_le_array(value):
+    a = np.asarray(value)
+    if a.dtype.kind == "U":
+        a = np.char.encode(a, "utf-8")
+    if a.dtype.kind == "S":
+        return a.astype(f"S{a.dtype.itemsize + 1}")        # room for the terminating NUL
+    if a.dtype.kind == "b":
+        return a.astype("<u1")
+    if a.dtype.kind not in "iuf":
+        raise H5FormatError(f"cannot write dtype {a.dtype}")
+    return a.astype(a.dtype.newbyteorder("<"))            # (tobytes() below always emits C order)
+
+
+def write_h5(path, datasets: dict, attrs: dict | None = None):
+    """Write root-level datasets (numeric scalars/arrays, C order as given) and root attributes
+    (strings or numeric scalars) as an HDF5 file in the dialect described in the module header.
+    File layout: superblock | root object header | B-tree node | local heap | symbol node |
+    per dataset: object header, raw data."""
+    names = sorted(datasets, key=lambda n: n.encode("utf-8"))          # symbol nodes are strcmp-sorted
+    if any("/" in n or not n for n in names):
+        raise H5FormatError("write_h5 writes root-level datasets only")
+    LEAF_K, INTERNAL_K = max(4, (len(names) + 1) // 2 + 1), 16         # one symbol node holds 2*LEAF_K
+
+    # local heap data: offset 0 is the empty string, then the names, each padded to 8 bytes
+    heap, name_off = bytearray(b"\0" * 8), {}
+    for n in names:
+        name_off[n] = len(heap)
+        heap += _pad8(n.encode("utf-8") + b"\0")
+    heap += b"\0" * 16                                                 # one free block (offset, size)
+    free_off = len(heap) - 16
+    struct.pack_into("<QQ", heap, free_off, 1, 16)                     # H5HL_FREE_NULL, block size
+
+    attr_msgs = []
+    for k, v in (attrs or {}).items():
+        a = _as_le_array(v)
+        tmsg, smsg = _dtype_message(a.dtype), _dataspace_message(a.shape)
+        nm = k.encode("utf-8") + b"\0"
+        attr_msgs.append(_message(0x000C, struct.pack("<BBHHH", 1, 0, len(nm), len(tmsg), len(smsg))
+                                  + _pad8(nm) + _pad8(tmsg) + _pad8(smsg) + a.tobytes()))
+
+    SUPER = 96
+    root_hdr_len = len(_object_header([_message(0x0011, b"\0" * 16)] + attr_msgs))
+    btree_at = SUPER + root_hdr_len
+    btree_len = 24 + (2 * INTERNAL_K + 1) * 8 + 2 * INTERNAL_K * 8
+    heap_at = btree_at + btree_len
+    heap_data_at = heap_at + 32
+    snod_at = heap_data_at + len(heap)
+    snod_len = 8 + 2 * LEAF_K * 40
+    pos = snod_at + snod_len
+
+    # datasets
+    blobs, entries = [], []
+    for n in names:
+        a = _as_le_array(datasets[n])
+        data = a.tobytes()
+        layout = struct.pack("<BBQQ", 3, 1, 0, len(data))              # address patched below
+        # same message set as libhdf5's own files: dataspace, datatype, fill value (v2: late
+        # allocation, write-if-set, defined, size 0), contiguous layout v3
+        head = [_message(0x0001, _dataspace_message(a.shape)), _message(0x0003, _dtype_message(a.dtype)),
+                _message(0x0005, struct.pack("<BBBBI", 2, 2, 2, 1, 0))]
+        data_at = pos + len(_object_header(head + [_message(0x0008, layout)]))
+        layout = struct.pack("<BBQQ", 3, 1, data_at if data else UNDEF, len(data))
+        hdr = _object_header(head + [_message(0x0008, layout)])
+        entries.append((name_off[n], pos))
+        blobs.append(hdr + _pad8(data))
+        pos = data_at + len(_pad8(data))
+    eof = pos
+
+    root_hdr = _object_header([_message(0x0011, struct.pack("<QQ", btree_at, heap_at))] + attr_msgs)
+    assert len(root_hdr) == root_hdr_len
+    sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBBBBBB", 0, 0, 0, 0, 0, 8, 8, 0)
+    sb += struct.pack("<HHI", LEAF_K, INTERNAL_K, 0)
+    sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
+    sb += struct.pack("<QQII", 0, SUPER, 1, 0) + struct.pack("<QQ", btree_at, heap_at)
+    assert len(sb) == SUPER
+
+    btree = b"TREE" + struct.pack("<BBH", 0, 0, 1 if names else 0) + struct.pack("<QQ", UNDEF, UNDEF)
+    btree += struct.pack("<Q", 0)                                      # key 0: the empty name
+    if names:
+        btree += struct.pack("<QQ", snod_at, name_off[names[-1]])      # child, key 1 = largest name
+    btree += b"\0" * (btree_len - len(btree))
+    heap_hdr = b"HEAP" + struct.pack("<BBBB", 0, 0, 0, 0) + struct.pack("<QQQ", len(heap), free_off, heap_data_at)
+    snod = b"SNOD" + struct.pack("<BBH", 1, 0, len(names))
+    for noff, ohdr in entries:
+        snod += struct.pack("<QQII", noff, ohdr, 0, 0) + b"\0" * 16
+    snod += b"\0" * (snod_len - len(snod))
+
+    with open(path, "wb") as fh:
+        fh.write(sb + root_hdr + btree + heap_hdr + bytes(heap) + snod + b"".join(blobs))

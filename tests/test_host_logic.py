@@ -150,3 +150,94 @@ def test_minih5_row_ranges_equal_the_full_read():
     assert np.array_equal(h.read_rows("system/coords", 0, 1), h.read("system/coords"))
     with pytest.raises(ValueError):
         h.read_rows("electron_repulsion_bbbb", 3, 12)
+
+
+# ---- result dump (reference src/util/dump_molsturm_hdf5.jl) ----------------------------------
+def test_h5_writer_round_trips_through_the_reader(tmp_path):
+    from scf_b200.minih5 import MiniH5, write_h5, _dtype_message
+    rng = np.random.default_rng(3)
+    data = {"n_alpha": np.int64(2), "restricted": np.uint8(1), "energy": -14.4868202421763,
+            "overlap_bb": rng.standard_normal((6, 6)), "orben_f": rng.standard_normal(12),
+            "ints": np.arange(5), "f32": np.float32(2.5), "fortran": np.asfortranarray(rng.standard_normal((3, 4)))}
+    path = str(tmp_path / "t.h5")
+    write_h5(path, data, {"format_version": "0.1.0", "format_type": "hdf5", "n": np.int64(7)})
+    h = MiniH5(path)
+    assert h.keys() == sorted(data)
+    assert h.attrs() == {"format_version": "0.1.0", "format_type": "hdf5", "n": 7}
+    for k, v in data.items():
+        r = h.read(k)
+        assert r.shape == np.shape(v) and r.dtype == np.asarray(v).dtype and np.array_equal(r, v)
+    assert np.array_equal(h.read_rows("overlap_bb", 2, 5), data["overlap_bb"][2:5])
+    many = {f"k{i:03d}": np.full(2, i) for i in range(70)}     # more names than a default symbol node holds
+    write_h5(path, many)
+    h = MiniH5(path)
+    assert h.keys() == sorted(many) and all(h.read(k)[0] == int(k[1:]) for k in many)
+    write_h5(path, {})
+    assert MiniH5(path).keys() == []
+    with pytest.raises(Exception):
+        write_h5(path, {"a/b": np.zeros(2)})
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DATA), reason="reference checkout not present")
+def test_h5_writer_encodes_datatypes_like_libhdf5():
+    """The datatype messages of the writer are byte-identical to the ones libhdf5 wrote into the
+    reference's integral dumps (f8, u8, i8) — the one cross-check against a real HDF5 file that is
+    possible without an HDF5 library."""
+    from scf_b200.minih5 import MiniH5, _dtype_message
+    h = MiniH5(os.path.join(REF_DATA, "integrals_be_3-21g.hdf5"))
+    for path, dt in (("kinetic_bb", "<f8"), ("system/nelec", "<u8"), ("system/atom_numbers", "<i8")):
+        ref = [bytes(p) for t, _, p in h._messages(h._lookup(path)["ohdr"] + h.base) if t == 0x0003][0]
+        mine = _dtype_message(np.dtype(dt))
+        assert ref[:len(mine)] == mine and not any(ref[len(mine):])
+
+
+@pytest.mark.parametrize("restricted", [True, False])
+def test_dump_molsturm_hdf5_contents(golden_dir, tmp_path, restricted):
+    """dump_molsturm_hdf5.jl:83-143 on a converged Be/3-21G result (the oracle's SCF stands in for
+    run_scf here; the GPU path produces the same dict)."""
+    from scf_b200.dump import dump_molsturm_hdf5, build_ab_matrix, concat_spin
+    from scf_b200.minih5 import MiniH5
+    system, integrals = o.load_integral_npz(os.path.join(golden_dir, "integrals_be_3-21g.npz"))
+    problem = o.assemble_hf_problem(system, integrals, restricted=restricted)
+    guess = o.compute_guess_hcore(problem)
+    res = o.run_scf(problem, guess)
+    assert res["converged"]
+    da, db = res["density"][:, :, 0], res["density"][:, :, -1]
+    ej, ek = o.termwise_jk_energies(integrals["electron_repulsion_bbbb"], np.stack([da, db], axis=2))
+    res["energies"].update(coulomb=ej, exchange=ek, nuclear_repulsion=0.0,
+                           kinetic=float(np.sum((da + db) * integrals["kinetic_bb"])),
+                           nuclear_attraction=float(np.sum((da + db) * integrals["nuclear_attraction_bb"])))
+    path = str(tmp_path / "state.hdf5")
+    dump_molsturm_hdf5(integrals, res, path)
+    h = MiniH5(path)
+    assert h.attrs() == {"format_version": "0.1.0", "format_type": "hdf5"}
+    expected = {"n_alpha", "n_beta", "n_bas", "restricted", "overlap_bb", "n_orbs_alpha", "n_orbs_beta",
+                "orben_f", "fock_bb", "fock_ff", "hcore_ff", "orbcoeff_bf", "n_mtx_applies", "n_iter",
+                "energy_coulomb", "energy_exchange", "energy_kinetic", "energy_nuclear_attraction",
+                "energy_nuclear_repulsion", "energy_ground_state", "final_1e_energy_change",
+                "final_error_norm", "final_tot_energy_change"}
+    assert set(h.keys()) == expected
+    n, n_orb = 9, problem.n_orb
+    assert h.read("n_alpha") == 2 and h.read("n_beta") == 2 and h.read("n_bas") == n
+    assert h.read("restricted") == int(restricted) and h.read("restricted").dtype == np.uint8
+    assert h.read("n_iter") == res["n_iter"] and np.isnan(h.read("n_mtx_applies"))
+    assert abs(h.read("energy_ground_state") - (-14.4868202421763)) < 1e-8
+    # the file holds Julia's column-major bytes under reversed dims: a C-order reader sees the transpose
+    s2 = h.read("overlap_bb")
+    assert s2.shape == (2 * n, 2 * n) and np.array_equal(s2[:n, :n], problem.overlap.T) and not s2[:n, n:].any()
+    assert np.array_equal(h.read("orben_f"), concat_spin(res["orben"]))
+    cbf = h.read("orbcoeff_bf")                       # Julia (2 n_orb, n_bas) -> file (n_bas, 2 n_orb)
+    assert cbf.shape == (n, 2 * n_orb) and np.array_equal(cbf[:, :n_orb], res["orbcoeff"][:, :, 0])
+    assert np.array_equal(cbf[:, n_orb:], res["orbcoeff"][:, :, -1])
+    # in the orbital basis a converged Fock matrix is diagonal with the orbital energies on it — to
+    # the SCF threshold only: the returned orbitals diagonalise the previous (extrapolated) Fock
+    # matrix, not the returned one (run_scf.jl:40 vs :48)
+    fff = h.read("fock_ff")
+    assert fff.shape == (2 * n_orb, 2 * n_orb)
+    assert np.abs(np.diag(fff) - concat_spin(res["orben"])).max() < 1e-4
+    assert np.abs(fff - np.diag(np.diag(fff))).max() < 1e-4
+    assert np.array_equal(h.read("fock_bb"), build_ab_matrix(res["fock"]).T)
+    e = res["energies"]
+    assert abs(e["kinetic"] + e["nuclear_attraction"] + e["coulomb"] + e["exchange"] - e["total"]) < 1e-7
+    with pytest.raises(NotImplementedError):
+        dump_molsturm_hdf5(integrals, res, path, export_eri_bbbb=True)

@@ -333,3 +333,25 @@ def test_misaligned_device_density_pointer_is_refused():
     out = d_out.cpu().numpy().reshape(n, n).T
     assert np.abs(out - ref[:, :, 0]).max() < 1e-12 * np.abs(ref).max()
     b.close()
+
+
+def test_example_driver_writes_molsturm_hdf5(golden_dir, tmp_path):
+    """examples/HartreeFock.jl:131-133: an <outfile> that is not .npz is written by
+    dump_molsturm_hdf5 (src/util/dump_molsturm_hdf5.jl) — read back with the package's reader.
+    (Like the test above it, not yet run on a B200; the dump itself is CPU-tested.)"""
+    import subprocess
+    import sys
+    from scf_b200.minih5 import MiniH5
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dump = os.path.join(golden_dir, "integrals_be_3-21g.npz")
+    out = tmp_path / "state.hdf5"
+    p = subprocess.run([sys.executable, os.path.join(root, "examples", "HartreeFock.py"), "--unrestricted",
+                        dump, str(out)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    h = MiniH5(str(out))
+    assert h.attrs()["format_type"] == "hdf5" and h.read("restricted") == 0 and h.read("n_bas") == 9
+    assert abs(h.read("energy_ground_state") - (-14.4868202421763)) < 1e-9 * 14.49
+    parts = sum(float(h.read("energy_" + k)) for k in ("coulomb", "exchange", "kinetic",
+                                                       "nuclear_attraction", "nuclear_repulsion"))
+    assert abs(parts - float(h.read("energy_ground_state"))) < 1e-6
+    assert h.read("orbcoeff_bf").shape == (9, 18) and h.read("fock_ff").shape == (18, 18)
