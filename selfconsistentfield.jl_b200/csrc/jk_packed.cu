@@ -19,21 +19,23 @@
 //   K'[i,k] += f D[j,l]   K'[i,l] += f D[j,k]   K'[j,k] += f D[i,l]   K'[j,l] += f D[i,k]
 // and K = K' + K'^T.  2 + 4 n_spin FMAs per 8 bytes: still HBM-bound (1.5-2.5 flop/B).
 //
-// Mapping (details at `packed_item`): one warp = one CTA owns (i, chunk of KC = 8 consecutive
+// Mapping (details at `packed_item`): one warp = one CTA owns (i, chunk of KC consecutive
 // k <= i, 64 consecutive l); each lane owns an l-PAIR (16 bytes per k and row) and the warp loops
 // over the rows j = 0..i, each of which contributes contiguous runs of the packed row.
-//   * all per-row data (ERI pairs from HBM, the density row from L2) travels through a 4-row
-//     cp.async (LDGSTS) ring in shared memory, three rows ahead of its use;
+//   * all per-row data (ERI pairs from HBM, the density row from L2) travels through a DEPTH-row
+//     cp.async (LDGSTS) ring in shared memory, DEPTH-1 rows ahead of its use; the row loop is
+//     unrolled DEPTH times so every ring and tile address is a compile-time offset;
 //   * sums whose output does not depend on j (K'[i,k], K'[i,l], J~[q]) stay in registers for the
 //     whole item; K'[j,l] is lane-private (one RED per lane and row); the lane-reductions
-//     (K'[j,k], J~[p]) go through a conflict-free shared-memory tile flushed every few rows;
+//     (K'[j,k], J~[p]) go through a conflict-free shared-memory tile flushed every DEPTH rows;
 //   * warps never synchronise with each other; cross-warp combination is fp64 RED.ADD into
 //     zeroed accumulators, so the packed path is deterministic only up to summation order
 //     (well inside the 1e-12 relative gate).
-// Compile-time knobs SCFB_EXP_NO_Z / SCFB_EXP_NO_FLUSH remove one cost centre each (wrong
-// results!) and exist only to reproduce the ablation in profiles/README.md.
+// The l-blocks of one (i, k-chunk) are neighbours in launch order and walk the rows in the same
+// order, so the 64-byte DRAM atoms two neighbours share are fetched once (second one hits L2).
 #include "scfb_internal.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -41,11 +43,8 @@ namespace {
 
 // One warp per CTA: the warps of an item never cooperate, and in the triangular iteration space
 // multi-warp CTAs keep dead warps' slots (and their shared memory) pinned until the longest
-// warp finishes; with LB = 32 every resident CTA is a live warp (measured 5.6 -> 4.9 ms).
-#ifndef SCFB_LB
-#define SCFB_LB 32
-#endif
-constexpr int LB = SCFB_LB;  // threads per CTA = LB/32 independent warps, 2*LB l values
+// warp finishes; with one-warp CTAs every resident CTA is a live warp (measured 5.6 -> 4.9 ms).
+constexpr int LB = 32;  // threads per CTA; 2*LB l values
 
 __host__ __device__ __forceinline__ uint64_t tri(uint64_t i) { return i * (i + 1) / 2; }
 __host__ __device__ __forceinline__ uint64_t seg_off(uint64_t k) { return tri(k) + (k + 1) / 2; }
@@ -105,716 +104,405 @@ __device__ __forceinline__ bool transpose_reduce_owner(int lane) {
   return V == 8 ? (lane & 3) == 0 : (lane & 7) == 0;
 }
 
-// One work item of one warp.  D: (n*n + DPAD) x NSPIN symmetric, padded so that the KC-wide
-// uniform reads D[j, k0..k0+KC) and the pair reads D[j, l0..l0+1] never leave the allocation;
-// dq2: 2*Dtot in pair space, stored with the SAME padded segment offsets seg_off(k)+l (pads
-// zero).  Kp: (n*n + DPAD) x NSPIN accumulators; Jp: accumulators indexed like dq2.
-// MODE 0: interior warp — every lane's pair lies inside every segment of the chunk: no predicates
-// MODE 1: edge warp — per-(t, lane) validity fixed for the item
-// MODE 2: diagonal chunk (k == i inside) — validity also depends on the row j
-//
-// Row sums over the lanes (K'[j,k] and J~[pr(i,j)]) do not use shuffles: every row each lane
-// parks its NV = NSPIN*KC + 1 partial sums in a per-warp shared-memory tile (conflict-free
-// STS), and once RB = 32/NV rows are parked lane r*NV+v adds the 32 partials of (row r,
-// value v) with 16 conflict-free LDS.128 (row stride 34 doubles) in a fixed order and issues
-// the RED.  That is ~13 instructions per row instead of ~56 for shuffle butterflies.
+// D: (n*n + DPAD) x NSPIN symmetric, padded so that the KC-wide uniform reads D[j, k0..k0+KC)
+// and the pair reads D[j, l0..l0+1] never leave the allocation; dq2: 2*Dtot in pair space,
+// stored with the SAME padded segment offsets seg_off(k)+l (pads zero).  Kp: (n*n + DPAD) x
+// NSPIN accumulators; Jp: accumulators indexed like dq2.
 constexpr int DPAD = 64;
-constexpr int YS = 34;  // padded lane stride of the row-sum tile (doubles)
-constexpr int DEPTH = 4;  // cp.async ring depth (rows)
-// rows parked in the row-sum tile between flushes, and doubles per row of the uniform-D ring
-__host__ __device__ constexpr int packed_rb(int nspin, int kc) {
-  return 32 / (nspin * kc + 1) < 4 ? 32 / (nspin * kc + 1) : 4;
+constexpr int YS = 34;    // padded lane stride of the row-sum tile (doubles)
+
+// shared memory of one warp, in doubles
+// DEPTH: cp.async ring depth (row pairs) == row pairs parked between flushes == unroll
+template <int NSPIN, int KC, int DEPTH>
+struct PkSmem {
+  static constexpr int NK = NSPIN * KC;
+  static constexpr int NV = NK + 2;  // lane-reduced values per row pair: K'[j,k] per spin and k, J~[(iA,j)], J~[(iB,j)]
+  static_assert(DEPTH * NV <= 32, "one flush pass: one lane per (row, value)");
+  static constexpr int DKN = (NK + 3) & ~1;  // D[j, k-chunk] per spin + 2Dtot[(iA,j)] + 2Dtot[(iB,j)], padded even
+  static constexpr int TILE = 0;                                // [DEPTH][NV][YS]
+  static constexpr int RING = TILE + DEPTH * NV * YS;           // [DEPTH][2][KC][32] double2
+  static constexpr int RING_DL = RING + DEPTH * 2 * KC * 64;    // [DEPTH][NSPIN][32] double2
+  static constexpr int RING_DK = RING_DL + DEPTH * NSPIN * 64;  // [DEPTH][DKN]
+  static constexpr int TOTAL = RING_DK + DEPTH * DKN;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t nbytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
 }
-__host__ __device__ constexpr int packed_dkn(int nspin, int kc) { return (nspin * kc + 2) & ~1; }
-__host__ __device__ constexpr size_t packed_smem_bytes(int nspin, int kc) {
-  return (size_t)(LB / 32) * packed_rb(nspin, kc) * (nspin * kc + 1) * YS * sizeof(double)  // row-sum tiles
-         + (size_t)DEPTH * kc * LB * 16                                                    // ERI ring
-         + (size_t)DEPTH * nspin * LB * 16                                                 // D[j,l] ring
-         + (size_t)DEPTH * (LB / 32) * packed_dkn(nspin, kc) * sizeof(double);             // D[j,k], 2Dtot ring
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
 
-template <int NSPIN, int KC, int MODE, bool VECD>
-__device__ __forceinline__ void packed_item(const double* __restrict__ eri_i,  // row (i,0)
+// One work item of one warp: TWO consecutive first indices iA, iB = iA + 1 (stream A = rows
+// (iA, j), stream B = rows (iB, j); `has_b` false for a shard's unpaired last index), one chunk of
+// KC consecutive k and 64 consecutive l.  Row j of both streams is consumed together: every output
+// indexed by j — K'[j,k] (a 32-lane reduction per k), K'[j,l] (a RED per lane) — and every per-row
+// load (D[j,l], D[j,k]) is then paid once per TWO packed rows, which is what bounds this kernel
+// (LSU wavefronts, instruction issue and L2 atomics, not DRAM).
+// MODE 0: interior warp — every lane's pair lies inside every segment of the chunk of both streams
+// MODE 1: edge warp — per-(t, lane) validity fixed for the item
+// MODE 2: the chunk reaches iA — validity also depends on the stream and on the row j
+//
+// Row sums over the lanes (K'[j,k], J~[pr(iA,j)], J~[pr(iB,j)]) do not use shuffles: every row
+// pair each lane parks its NV partial sums in the warp's shared-memory tile (conflict-free STS),
+// and once DEPTH row pairs are parked lane r*NV+v adds the 32 partials of (row r, value v) with
+// 16 conflict-free LDS.128 (row stride 34 doubles) in a fixed order and issues the RED.
+template <int NSPIN, int KC, int DEPTH, int MODE, bool VECD>
+__device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  // row (iA,0)
+                                            const double* __restrict__ eri_b,  // row (iB,0)
                                             const double* __restrict__ D, size_t dstride,
                                             const double* __restrict__ dq2,
                                             double* __restrict__ Kp, double* __restrict__ Jp,
-                                            double* __restrict__ ys,  // this warp's 32*YS tile
-                                            double2* __restrict__ ring,     // ERI ring, this thread's slot 0
-                                            double2* __restrict__ ring_dl,  // D[j,l-pair] ring, this thread's slot 0
-                                            double* __restrict__ ring_dk,   // this warp's [DEPTH][DKN] block
-                                            int n, int i, int k0, int l0, int lane, uint32_t rot) {
-  constexpr int NV = NSPIN * KC + 1;
-  constexpr int RB = packed_rb(NSPIN, KC);
-  constexpr int DKN = packed_dkn(NSPIN, KC);
-  const int kmax = min(k0 + KC - 1, i);
+                                            double* __restrict__ sm,  // this warp's PkSmem block
+                                            int n, int iA, bool has_b, int k0, int l0, int lane,
+                                            uint32_t rot) {
+  using S = PkSmem<NSPIN, KC, DEPTH>;
+  constexpr int NK = S::NK, NV = S::NV, DKN = S::DKN;
+  const int iB = iA + 1;
+  const int iT = has_b ? iB : iA;  // largest first index of the item
+  const int kmax = min(k0 + KC - 1, iT);
   // lanes past the triangle edge (l > kmax, possibly l >= n) only feed zeros
   const bool l0_in = MODE == 0 || l0 <= kmax, l1_in = MODE == 0 || l0 + 1 <= kmax;
   const int lc = l0_in ? l0 : 0;
-  const uint64_t Ei = seg_off(i);  // elements of the full segments 0..i-1 of every row (i,*)
+  const uint64_t EA = seg_off(iA), EB = seg_off(iB);  // elements of the full segments 0..i-1 of every row (i,*)
+
+  // shared-memory addresses of this lane's slots (stage / value offsets are immediates below)
+  const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(sm);
+  const uint32_t ring_a = sm_base + (S::RING + 2 * lane) * 8;        // + ((stage*2 + stream)*KC + t) * 512
+  const uint32_t ring_dl_a = sm_base + (S::RING_DL + 2 * lane) * 8;  // + (stage*NSPIN + s) * 512
+  const uint32_t ring_dk_a = sm_base + (S::RING_DK + lane) * 8;      // + stage*DKN*8   (lanes < NK + 2)
+  const double2* ring = reinterpret_cast<const double2*>(sm + S::RING) + lane;
+  const double2* ring_dl = reinterpret_cast<const double2*>(sm + S::RING_DL) + lane;
+  const double* ring_dk = sm + S::RING_DK;
+  double* ys = sm + S::TILE;
 
   // per-item constants
-  double di_l[NSPIN][2], di_k[NSPIN][KC], dq[KC][2];
-  uint32_t off[KC];  // element offset of this lane's pair inside a row, per k of the chunk
-  bool ok[KC];
+  double dA_l[NSPIN][2], dB_l[NSPIN][2], dA_k[NSPIN][KC], dB_k[NSPIN][KC], dq[KC][2];
+  uint32_t off[KC];  // BYTE offset of this lane's pair inside a row, per k of the chunk (same for both streams)
+  bool okA[KC], okB[KC];
 #pragma unroll
   for (int s = 0; s < NSPIN; ++s) {
-    const double* di = D + s * dstride + (size_t)i * n;
-    di_l[s][0] = __ldg(di + lc);
-    di_l[s][1] = __ldg(di + lc + 1);  // beyond-the-edge values only ever meet zero ERI entries
+    const double* da = D + s * dstride + (size_t)iA * n;
+    const double* db = D + s * dstride + (size_t)iT * n;
+    dA_l[s][0] = __ldg(da + lc);
+    dA_l[s][1] = __ldg(da + lc + 1);  // beyond-the-edge values only ever meet zero ERI entries
+    dB_l[s][0] = __ldg(db + lc);
+    dB_l[s][1] = __ldg(db + lc + 1);
   }
 #pragma unroll
   for (int t = 0; t < KC; ++t) {
     const int k = k0 + t;
-    ok[t] = MODE == 0 || (k <= i && l0 <= k);
-    const int kc = k <= i ? k : i;
-    off[t] = (uint32_t)seg_off(kc) + (uint32_t)lc;
+    okA[t] = MODE == 0 || (k <= iA && l0 <= k);
+    okB[t] = MODE == 0 || (has_b && k <= iB && l0 <= k);
+    const int kc = k <= iT ? k : iT;
+    const uint32_t o = (uint32_t)seg_off(kc) + (uint32_t)lc;
+    off[t] = o * 8u;
     const double2 q2 =
-        ok[t] ? __ldg(reinterpret_cast<const double2*>(dq2 + off[t])) : make_double2(0.0, 0.0);
+        (okA[t] || okB[t]) ? __ldg(reinterpret_cast<const double2*>(dq2 + o)) : make_double2(0.0, 0.0);
     dq[t][0] = q2.x;
     dq[t][1] = q2.y;
 #pragma unroll
-    for (int s = 0; s < NSPIN; ++s) di_k[s][t] = __ldg(D + s * dstride + (size_t)i * n + kc);
+    for (int s = 0; s < NSPIN; ++s) {
+      dA_k[s][t] = __ldg(D + s * dstride + (size_t)iA * n + kc);
+      dB_k[s][t] = __ldg(D + s * dstride + (size_t)iT * n + kc);
+    }
   }
 
-  double a1[NSPIN][KC], a2[NSPIN][2], jq[KC][2];
+  double a1A[NSPIN][KC], a1B[NSPIN][KC], a2A[NSPIN][2], a2B[NSPIN][2], jq[KC][2];
 #pragma unroll
   for (int t = 0; t < KC; ++t) {
     jq[t][0] = jq[t][1] = 0.0;
 #pragma unroll
-    for (int s = 0; s < NSPIN; ++s) a1[s][t] = 0.0;
+    for (int s = 0; s < NSPIN; ++s) a1A[s][t] = a1B[s][t] = 0.0;
   }
 #pragma unroll
-  for (int s = 0; s < NSPIN; ++s) a2[s][0] = a2[s][1] = 0.0;
+  for (int s = 0; s < NSPIN; ++s) a2A[s][0] = a2A[s][1] = a2B[s][0] = a2B[s][1] = 0.0;
 
-  const int rows = i + 1;
-  // Everything a row needs travels global -> shared with cp.async (LDGSTS) into a DEPTH-deep
-  // ring, DEPTH-1 rows ahead of its use, so neither the HBM latency of the ERI pairs nor the
-  // L2 latency of the density row (L1 cannot hold D) sits on a row's critical path and no
-  // registers are tied up:  ERI pairs and D[j, l-pair] go to slots only the issuing thread reads
-  // back; the warp-uniform D[j, k0..k0+KC) and 2Dtot[(i,j)] are fetched by the first lanes and
-  // read back as shared-memory broadcasts after a __syncwarp().
-  auto issue_row = [&](int stage, const double* row, const double* dj0, const double* dqp, int j) {
+  const int rows = iT + 1;  // stream A has no row j = iB
+  // Rows are visited in a rotated order that differs per (i, k-chunk), so that concurrently
+  // running warps do not all RED into the same K'[j,:] row at the same time; the l-blocks of one
+  // (i, k-chunk) share the order (their reads of a row are neighbours in memory).
+  const int j_first = (int)(rot % (uint32_t)rows);
+
+  // ---- load side: row pair jl goes to the ring DEPTH-1 pairs ahead of its use (warp-uniform state) ----
+  int jl = j_first;
+  // row (i,j+1) starts E(i) + ceil2(j+1) elements after row (i,j); stream A's pointer is only
+  // dereferenced while jl <= iA
+  const char* rowA = reinterpret_cast<const char*>(eri_a + (uint64_t)jl * EA + seg_off(jl));
+  const char* rowB = reinterpret_cast<const char*>(eri_b + (uint64_t)jl * EB + seg_off(jl));
+  const uint32_t stepA = (uint32_t)EA * 8u, stepB = (uint32_t)EB * 8u;
+  // per-lane source of the warp-uniform values: lanes < NK fetch D[j, k0 + t] of spin s, lane NK
+  // 2Dtot[(iA,j)], lane NK+1 2Dtot[(iB,j)]:  src = dk_base + j * dk_step
+  const double* dk_base;
+  uint32_t dk_step;
+  {
+    const int s = lane / KC, t = lane - s * KC;
+    dk_base = lane < NK ? D + s * dstride + k0 + t : (lane == NK ? dq2 + EA : dq2 + (has_b ? EB : EA));
+    dk_step = lane < NK ? (uint32_t)n : 1u;
+  }
+  const double* dl_base = D + lc;
+  // Everything a row pair needs travels global -> shared with cp.async (LDGSTS), so neither the
+  // HBM latency of the ERI pairs nor the L2 latency of the density row (L1 cannot hold D) sits on
+  // the critical path and no registers are tied up: ERI pairs and D[j, l-pair] go to slots only the
+  // issuing thread reads back; the warp-uniform values are fetched by the first lanes and read
+  // back as shared-memory broadcasts after a __syncwarp().
+  auto issue_row = [&](const int stage) {  // `stage` is a compile-time constant after unrolling
+    const bool rowA_in = jl <= iA;
 #pragma unroll
     for (int t = 0; t < KC; ++t) {
-      const bool valid = MODE == 0 ? true : (MODE == 2 ? (ok[t] && (k0 + t < i || l0 <= j)) : ok[t]);
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (stage * KC + t) * LB);
-      const uint32_t nbytes = valid ? 16u : 0u;  // 0 -> the 16 bytes are zero-filled
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(row + off[t]),
-                   "r"(nbytes)
-                   : "memory");
+      const uint32_t dstA = ring_a + ((stage * 2 + 0) * KC + t) * 512;
+      const uint32_t dstB = ring_a + ((stage * 2 + 1) * KC + t) * 512;
+      bool vA = rowA_in, vB = has_b;
+      if (MODE != 0) {
+        vA = vA && okA[t] && (MODE != 2 || k0 + t < iA || l0 <= jl);
+        vB = vB && okB[t] && (MODE != 2 || k0 + t < iB || l0 <= jl);
+      }
+      cp_async16(dstA, rowA + off[t], vA ? 16u : 0u);  // 0 -> the 16 bytes are zero-filled
+      cp_async16(dstB, rowB + off[t], vB ? 16u : 0u);
     }
+    const double* dj_l = dl_base + (size_t)jl * n;  // D[j, l-pair]   (+ s*dstride per spin)
 #pragma unroll
     for (int s = 0; s < NSPIN; ++s) {
-      const double* src = dj0 + s * dstride + lc;
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring_dl + (stage * NSPIN + s) * LB);
+      const uint32_t dst = ring_dl_a + (stage * NSPIN + s) * 512;
       if (VECD) {  // n even: (j*n + even) is 16-byte aligned
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        cp_async16(dst, dj_l + s * dstride);
       } else {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8), "l"(src + 1) : "memory");
+        cp_async8(dst, dj_l + s * dstride);
+        cp_async8(dst + 8, dj_l + s * dstride + 1);
       }
     }
-    if (lane <= NSPIN * KC) {
-      const int s = lane / KC, t = lane - s * KC;
-      const double* src = lane == NSPIN * KC ? dqp : dj0 + s * dstride + k0 + t;
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring_dk + stage * DKN + lane);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    if (lane < NK + 2) cp_async8(ring_dk_a + stage * DKN * 8, dk_base + (size_t)jl * dk_step);
+    // advance to the next row in the rotated order
+    if (jl + 1 == rows) {
+      jl = 0;
+      rowA = reinterpret_cast<const char*>(eri_a);
+      rowB = reinterpret_cast<const char*>(eri_b);
+    } else {
+      const uint32_t c2 = (uint32_t)((jl + 2) & ~1) * 8u;
+      rowA += stepA + c2;
+      rowB += stepB + c2;
+      ++jl;
     }
   };
 
-  // Rows are visited in a rotated order that differs per work item, so that concurrently
-  // running warps do not all RED into the same K'[j,:] row at the same time.
-  const int j_first = (int)(rot % (uint32_t)rows);
-  // load side (DEPTH-1 rows ahead), warp-uniform
-  int j = j_first;
-  const double* row = eri_i + (uint64_t)j * Ei + seg_off(j);
-  const double* dj0 = D + (size_t)j * n;  // D[j, :]   (+ s*dstride per spin)
-  const double* dqp = dq2 + Ei + j;       // 2 Dtot[(i,j)]
-  // consume side
-  int jc = j_first;                       // j of the row being consumed
-  double* kj0 = Kp + (size_t)jc * n;      // K'[j, :]  (+ s*dstride per spin)
-  int parked = 0;                         // rows parked in the tile
-  int j_tile = jc;                        // j of the first parked row
+  // ---- consume side ----
+  int jc = j_first;  // j of the row pair being consumed
+  const int red_r = lane / NV, red_v = lane - red_r * NV;  // lane r*NV + v reduces (row r, value v) of the tile
+  int j_tile = jc;                                         // j of the first parked row pair
 
-  // lane r*NV + v reduces (row r, value v) of the tile
-  const int red_r = lane / NV, red_v = lane - red_r * NV;
   auto flush_tile = [&](int n_rows) {
     __syncwarp();
-    if (red_r < n_rows) {  // (red_r < RB always holds for lanes < RB*NV)
+    if (red_r < n_rows) {  // (red_r < DEPTH always holds for lanes < DEPTH*NV)
       const double2* src = reinterpret_cast<const double2*>(ys + lane * YS);
-      double acc0 = 0.0, acc1 = 0.0;
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const double2 v = src[q];
-        acc0 += v.x;
-        acc1 += v.y;
+      for (int q = 0; q < 16; q += 2) {
+        const double2 u = src[q], v = src[q + 1];
+        acc[0] += u.x;
+        acc[1] += u.y;
+        acc[2] += v.x;
+        acc[3] += v.y;
       }
-      const double tot = acc0 + acc1;
+      const double tot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
       int jr = j_tile + red_r;
       if (jr >= rows) jr -= rows;
-      if (red_v == NV - 1) {
-        atomicAdd(Jp + Ei + jr, tot);  // J~[pr(i,j)]
+      if (red_v == NK) {
+        if (jr <= iA) atomicAdd(Jp + EA + jr, tot);  // J~[pr(iA,j)]
+      } else if (red_v == NK + 1) {
+        if (has_b) atomicAdd(Jp + EB + jr, tot);  // J~[pr(iB,j)]
       } else {
         const int sp = red_v / KC, t = red_v - sp * KC;
-        if (MODE == 0 || k0 + t <= i) atomicAdd(Kp + sp * dstride + (size_t)jr * n + k0 + t, tot);  // K'[j,k]
+        if (MODE == 0 || k0 + t <= iT) atomicAdd(Kp + sp * dstride + (size_t)jr * n + k0 + t, tot);  // K'[j,k]
       }
     }
     __syncwarp();
   };
 
-  auto consume = [&](int stage) {
-    double2 w[KC];
-#pragma unroll
-    for (int t = 0; t < KC; ++t) w[t] = ring[(stage * KC + t) * LB];
-    struct {
-      double dj_l[NSPIN][2], dj_k[NSPIN][KC], dp2;
-    } r;
+  auto consume = [&](const int stage) {  // compile-time constant; the row pair is parked in tile row `stage`
     const double* dk = ring_dk + stage * DKN;  // same address in every lane: broadcast reads
-    r.dp2 = dk[NSPIN * KC];
+    const double2 dp2 = *reinterpret_cast<const double2*>(dk + NK);  // 2Dtot[(iA,j)], 2Dtot[(iB,j)]
+    double dj_l[NSPIN][2];
 #pragma unroll
     for (int s = 0; s < NSPIN; ++s) {
-      const double2 v = ring_dl[(stage * NSPIN + s) * LB];
-      r.dj_l[s][0] = v.x;
-      r.dj_l[s][1] = v.y;
-#pragma unroll
-      for (int t = 0; t < KC; t += 2) {
-        const double2 u = *reinterpret_cast<const double2*>(dk + s * KC + t);
-        r.dj_k[s][t] = u.x;
-        r.dj_k[s][t + 1] = u.y;
-      }
+      const double2 v = ring_dl[(stage * NSPIN + s) * 32];
+      dj_l[s][0] = v.x;
+      dj_l[s][1] = v.y;
     }
-    double jp0 = 0.0, jp1 = 0.0;
+    double jpA = 0.0, jpB = 0.0;
     double z[NSPIN][2];
 #pragma unroll
     for (int s = 0; s < NSPIN; ++s) z[s][0] = z[s][1] = 0.0;
-    double* park = ys + parked * NV * YS + lane;
+    double* park = ys + stage * NV * YS + lane;
 #pragma unroll
-    for (int t = 0; t < KC; ++t) {
-      const double w0 = w[t].x, w1 = w[t].y;
-      jp0 = fma(w0, dq[t][0], jp0);
-      jp1 = fma(w1, dq[t][1], jp1);
-      jq[t][0] = fma(w0, r.dp2, jq[t][0]);
-      jq[t][1] = fma(w1, r.dp2, jq[t][1]);
+    for (int t = 0; t < KC; t += 2) {
+      double2 wA[2], wB[2];
 #pragma unroll
-      for (int s = 0; s < NSPIN; ++s) {
-        a1[s][t] = fma(w0, r.dj_l[s][0], a1[s][t]);
-        a1[s][t] = fma(w1, r.dj_l[s][1], a1[s][t]);
-        a2[s][0] = fma(w0, r.dj_k[s][t], a2[s][0]);
-        a2[s][1] = fma(w1, r.dj_k[s][t], a2[s][1]);
-        park[(s * KC + t) * YS] = fma(w1, di_l[s][1], w0 * di_l[s][0]);  // -> K'[j,k]
-        z[s][0] = fma(w0, di_k[s][t], z[s][0]);
-        z[s][1] = fma(w1, di_k[s][t], z[s][1]);
+      for (int u = 0; u < 2; ++u) {
+        wA[u] = ring[((stage * 2 + 0) * KC + t + u) * 32];
+        wB[u] = ring[((stage * 2 + 1) * KC + t + u) * 32];
+      }
+      double2 dk2[NSPIN];
+#pragma unroll
+      for (int s = 0; s < NSPIN; ++s) dk2[s] = *reinterpret_cast<const double2*>(dk + s * KC + t);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const double x0 = wA[u].x, x1 = wA[u].y, y0 = wB[u].x, y1 = wB[u].y;
+        jpA = fma(x0, dq[t + u][0], jpA);
+        jpA = fma(x1, dq[t + u][1], jpA);
+        jpB = fma(y0, dq[t + u][0], jpB);
+        jpB = fma(y1, dq[t + u][1], jpB);
+        jq[t + u][0] = fma(x0, dp2.x, jq[t + u][0]);
+        jq[t + u][0] = fma(y0, dp2.y, jq[t + u][0]);
+        jq[t + u][1] = fma(x1, dp2.x, jq[t + u][1]);
+        jq[t + u][1] = fma(y1, dp2.y, jq[t + u][1]);
+#pragma unroll
+        for (int s = 0; s < NSPIN; ++s) {
+          const double djk = u ? dk2[s].y : dk2[s].x;
+          a1A[s][t + u] = fma(x0, dj_l[s][0], a1A[s][t + u]);
+          a1A[s][t + u] = fma(x1, dj_l[s][1], a1A[s][t + u]);
+          a1B[s][t + u] = fma(y0, dj_l[s][0], a1B[s][t + u]);
+          a1B[s][t + u] = fma(y1, dj_l[s][1], a1B[s][t + u]);
+          a2A[s][0] = fma(x0, djk, a2A[s][0]);
+          a2A[s][1] = fma(x1, djk, a2A[s][1]);
+          a2B[s][0] = fma(y0, djk, a2B[s][0]);
+          a2B[s][1] = fma(y1, djk, a2B[s][1]);
+          // -> K'[j,k]: both streams feed the same output
+          park[(s * KC + t + u) * YS] =
+              fma(y1, dB_l[s][1], fma(y0, dB_l[s][0], fma(x1, dA_l[s][1], x0 * dA_l[s][0])));
+          z[s][0] = fma(x0, dA_k[s][t + u], z[s][0]);
+          z[s][0] = fma(y0, dB_k[s][t + u], z[s][0]);
+          z[s][1] = fma(x1, dA_k[s][t + u], z[s][1]);
+          z[s][1] = fma(y1, dB_k[s][t + u], z[s][1]);
+        }
       }
     }
-    park[(NV - 1) * YS] = jp0 + jp1;  // -> J~[pr(i,j)]
-    // K'[j,l]: lane-private, one RED per lane and row (K' entries are accumulated at
+    park[NK * YS] = jpA;        // -> J~[pr(iA,j)]
+    park[(NK + 1) * YS] = jpB;  // -> J~[pr(iB,j)]
+    // K'[j,l]: lane-private, one RED per lane and row pair (K' entries are accumulated at
     // whichever of (a,b)/(b,a) coalesces: K = K' + K'^T does not care)
+    double* kj = Kp + (size_t)jc * n + l0;
 #pragma unroll
     for (int s = 0; s < NSPIN; ++s) {
-      double* kj = kj0 + s * dstride;
-#ifndef SCFB_EXP_NO_Z
-      if (l0_in) atomicAdd(kj + l0, z[s][0]);
-      if (l1_in) atomicAdd(kj + l0 + 1, z[s][1]);
-#else
-      a2[s][0] += z[s][0] + z[s][1];
-      (void)kj;
-#endif
+      if (l0_in) atomicAdd(kj + s * dstride, z[s][0]);
+      if (l1_in) atomicAdd(kj + s * dstride + 1, z[s][1]);
     }
-#ifdef SCFB_EXP_NO_FLUSH
-    parked = 0;
-#endif
-    if (++parked == RB) {
-      flush_tile(RB);
-      parked = 0;
-      j_tile = jc + 1 == rows ? 0 : jc + 1;
-    }
-    // next consumed row
-    if (jc + 1 == rows) {
-      jc = 0;
-      kj0 = Kp;
-    } else {
-      ++jc;
-      kj0 += n;
-    }
-  };
-  // row (i,j+1) starts E(i) + ceil2(j+1) elements after row (i,j); wraps to row (i,0)
-  auto advance = [&]() {
-    if (j + 1 == rows) {
-      j = 0;
-      row = eri_i;
-      dj0 = D;
-      dqp = dq2 + Ei;
-    } else {
-      row += Ei + ((j + 2) & ~1);
-      ++j;
-      dj0 += n;
-      ++dqp;
-    }
+    jc = jc + 1 == rows ? 0 : jc + 1;
   };
 
-  // prologue: DEPTH-1 rows in flight (empty groups keep the group count uniform)
-#pragma unroll
-  for (int d = 0; d < DEPTH - 1; ++d) {
-    if (d < rows) {
-      issue_row(d, row, dj0, dqp, j);
-      advance();
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  for (int step = 0; step < rows; ++step) {
-    if (step + DEPTH - 1 < rows) {
-      issue_row((step + DEPTH - 1) % DEPTH, row, dj0, dqp, j);
-      advance();
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  auto commit = [] { asm volatile("cp.async.commit_group;" ::: "memory"); };
+  auto wait_row = [] {
     asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
     __syncwarp();  // the uniform values were fetched by other lanes
-    consume(step % DEPTH);
+  };
+
+  // prologue: DEPTH-1 row pairs in flight (empty groups keep the group count uniform)
+  int to_issue = rows;
+#pragma unroll
+  for (int d = 0; d < DEPTH - 1; ++d) {
+    if (to_issue > 0) {
+      issue_row(d);
+      --to_issue;
+    }
+    commit();
   }
-  if (parked) flush_tile(parked);
+  int remaining = rows;
+  while (remaining >= DEPTH) {
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) {
+      if (to_issue > 0) {
+        issue_row((d + DEPTH - 1) % DEPTH);
+        --to_issue;
+      }
+      commit();
+      wait_row();
+      consume(d);
+    }
+    flush_tile(DEPTH);
+    j_tile = jc;
+    remaining -= DEPTH;
+  }
+  if (remaining > 0) {  // every remaining row pair is already in flight
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; ++d) {
+      if (d < remaining) {
+        commit();
+        wait_row();
+        consume(d);
+      }
+    }
+    flush_tile(remaining);
+  }
 
   // per-item outputs
 #pragma unroll
   for (int s = 0; s < NSPIN; ++s) {
-    double* ki = Kp + s * dstride + (size_t)n * i;
-    if (l0_in) atomicAdd(ki + l0, a2[s][0]);  // K'[i,l]
-    if (l1_in) atomicAdd(ki + l0 + 1, a2[s][1]);
-    const double r = warp_transpose_reduce<KC>(a1[s], lane);
+    double* ka = Kp + s * dstride + (size_t)n * iA;
+    if (l0_in) atomicAdd(ka + l0, a2A[s][0]);  // K'[iA,l]
+    if (l1_in) atomicAdd(ka + l0 + 1, a2A[s][1]);
+    const double ra = warp_transpose_reduce<KC>(a1A[s], lane);
     const int t = transpose_reduce_index<KC>(lane);
-    if (transpose_reduce_owner<KC>(lane) && k0 + t <= i) atomicAdd(ki + k0 + t, r);  // K'[i,k]
+    const bool owner = transpose_reduce_owner<KC>(lane);
+    if (owner && k0 + t <= iA) atomicAdd(ka + k0 + t, ra);  // K'[iA,k]
+    const double rb = warp_transpose_reduce<KC>(a1B[s], lane);
+    if (has_b) {
+      double* kb = ka + n;
+      if (l0_in) atomicAdd(kb + l0, a2B[s][0]);  // K'[iB,l]
+      if (l1_in) atomicAdd(kb + l0 + 1, a2B[s][1]);
+      if (owner && k0 + t <= iB) atomicAdd(kb + k0 + t, rb);  // K'[iB,k]
+    }
   }
 #pragma unroll
   for (int t = 0; t < KC; ++t)
-    if (ok[t]) {  // J~[q]; the pad slot only ever receives zeros
-      atomicAdd(Jp + off[t], jq[t][0]);
-      atomicAdd(Jp + off[t] + 1, jq[t][1]);
-    }
-}
-
-// grid = (n_kchunks, n_i_owned, n_lblocks), block = LB threads = 4 independent warps.
-template <int NSPIN, int KC, int MINB, bool VECD>
-__global__ void __launch_bounds__(LB, MINB)
-jk_packed_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Btab,
-                 uint64_t shard_offset, const double* __restrict__ D, size_t dstride,
-                 const double* __restrict__ dq2, double* __restrict__ Kp, double* __restrict__ Jp,
-                 int n, int i_lo) {
-  extern __shared__ __align__(16) unsigned char pk_smem[];
-  constexpr int TILE = packed_rb(NSPIN, KC) * (NSPIN * KC + 1) * YS;  // doubles per warp
-  constexpr int DKN = packed_dkn(NSPIN, KC);
-  double* ys_all = reinterpret_cast<double*>(pk_smem);                                // [warps][TILE]
-  double2* ring_all = reinterpret_cast<double2*>(ys_all + (LB / 32) * TILE);          // [DEPTH][KC][LB]
-  double2* ring_dl_all = ring_all + DEPTH * KC * LB;                                  // [DEPTH][NSPIN][LB]
-  double* ring_dk_all = reinterpret_cast<double*>(ring_dl_all + DEPTH * NSPIN * LB);  // [warps][DEPTH][DKN]
-  const int i = i_lo + blockIdx.y;
-  const int k0 = blockIdx.x * KC;
-  if (k0 > i) return;
-  const int m = blockIdx.z * LB + threadIdx.x;  // l-pair index
-  const int lane = threadIdx.x & 31;
-  const int kmax = min(k0 + KC - 1, i);
-  const int wl = 2 * (m & ~31);  // first l of this warp
-  if (wl > kmax) return;         // whole warp beyond the triangle
-  const int l0 = 2 * m;
-  const double* eri_i = eri + (Btab[i] - shard_offset);
-  double* ys = ys_all + (threadIdx.x >> 5) * TILE;
-  double2* ring = ring_all + threadIdx.x;
-  double2* ring_dl = ring_dl_all + threadIdx.x;
-  double* ring_dk = ring_dk_all + (threadIdx.x >> 5) * DEPTH * DKN;
-  const uint32_t rot =
-      blockIdx.x * 40503u + blockIdx.z * 9973u + blockIdx.y * 17u + (threadIdx.x >> 5) * 7u;
-  if (kmax == i)
-    packed_item<NSPIN, KC, 2, VECD>(eri_i, D, dstride, dq2, Kp, Jp, ys, ring, ring_dl, ring_dk, n, i, k0, l0, lane, rot);
-  else if (wl + 63 <= k0)
-    packed_item<NSPIN, KC, 0, VECD>(eri_i, D, dstride, dq2, Kp, Jp, ys, ring, ring_dl, ring_dk, n, i, k0, l0, lane, rot);
-  else
-    packed_item<NSPIN, KC, 1, VECD>(eri_i, D, dstride, dq2, Kp, Jp, ys, ring, ring_dl, ring_dk, n, i, k0, l0, lane, rot);
-}
-
-// ---- mbarrier / bulk-copy (TMA) helpers ----------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
-// ------------------------------------------------------------------------------------------
-// v5 (SCFB_PACKED_TMA=1): the one-warp work item of `packed_item`, fed by the TMA engine from a
-// DIFFERENT warp.  ncu on v2 shows the LSU data pipe at 66 % with two warps per scheduler: per
-// row and warp ~160 LSU cycles, 80 of them the LDGSTS writes of the ERI pairs and of the density
-// row.  v4 let lane 0 of the consuming warp post bulk copies instead (cp.async.bulk, SASS UBLKCP)
-// and lost: a bulk copy costs its issuer ~35 instructions / ~70 cycles
-// (benchmarks/micro/bulk_copy_rate.cu), ten of them per row came out of the consumer's own row
-// budget (7.0 vs 5.5 ms).  Here a CTA is WS_PAIRS independent (producer warp, consumer warp)
-// pairs: the producer draws work items from a global counter (heaviest i first), publishes them
-// to its consumer through a two-deep queue and posts, up to DEPTH rows ahead, one bulk copy per
-// k-segment (<= 512 B: the consumer's 64 l values), one per spin for D[j, wl..wl+63] and one per
-// spin for D[j, k0..k0+KC), all completing on the stage's "full" mbarrier; the consumer reads its
-// operands out of the stage, hands it back ("empty" mbarrier) and does the math of `packed_item`.
-// Pairs never synchronise with each other; the ring runs on across items.  setmaxnreg moves
-// registers from the producer warpgroups to the consumer warpgroups.  Requires n even.
-// ------------------------------------------------------------------------------------------
-constexpr int WS_PAIRS = 8;
-constexpr int WS_PRODUCER_REGS = 48, WS_CONSUMER_REGS = 208;  // 256 * (48 + 208) = 65536
-__host__ __device__ constexpr int ws_stage_doubles(int nspin, int kc) {
-  return kc * 64 + nspin * 64 + nspin * kc;
-}
-__host__ __device__ constexpr int ws_pair_doubles(int nspin, int kc) {
-  return packed_rb(nspin, kc) * (nspin * kc + 1) * YS + DEPTH * ws_stage_doubles(nspin, kc);
-}
-
-struct WsItem {
-  int i, k0, wl;
-  uint32_t rot;
-  bool valid;
-};
-// linear index -> item, heaviest rows first; kc fastest so that neighbours share D rows in L2
-template <int KC>
-__device__ __forceinline__ WsItem ws_decode(int idx, int n, int i_hi) {
-  const int nk = (n + KC - 1) / KC, nl = (n + 63) / 64;
-  const int per_i = nk * nl;
-  WsItem it;
-  it.i = i_hi - 1 - idx / per_i;
-  const int r = idx % per_i;
-  const int kc = r % nk, lw = r / nk;
-  it.k0 = kc * KC;
-  it.wl = lw * 64;
-  it.rot = (uint32_t)kc * 40503u + (uint32_t)lw * 9973u + (uint32_t)it.i * 17u;
-  it.valid = it.k0 <= it.i && it.wl <= min(it.k0 + KC - 1, it.i);
-  return it;
-}
-
-// consumer side of one work item; `sc` is the pair's running stage counter
-template <int NSPIN, int KC, int MODE>
-__device__ __forceinline__ void ws_consume_item(const double* __restrict__ D, size_t dstride,
-                                                const double* __restrict__ dq2,
-                                                double* __restrict__ Kp, double* __restrict__ Jp,
-                                                double* __restrict__ ys,
-                                                const double* __restrict__ stages,
-                                                uint64_t* __restrict__ full, uint64_t* __restrict__ empty,
-                                                int n, int i, int k0, int wl, int lane, uint32_t rot,
-                                                uint32_t& sc) {
-  constexpr int NV = NSPIN * KC + 1;
-  constexpr int RB = packed_rb(NSPIN, KC);
-  constexpr int STG = ws_stage_doubles(NSPIN, KC);
-  const int l0 = wl + 2 * lane;
-  const int kmax = min(k0 + KC - 1, i);
-  const bool l0_in = MODE == 0 || l0 <= kmax, l1_in = MODE == 0 || l0 + 1 <= kmax;
-  const int lc = l0_in ? l0 : 0;
-  const uint64_t Ei = seg_off(i);
-
-  double di_l[NSPIN][2], di_k[NSPIN][KC], dq[KC][2];
-  bool ok[KC];
-#pragma unroll
-  for (int s = 0; s < NSPIN; ++s) {
-    const double* di = D + s * dstride + (size_t)i * n;
-    di_l[s][0] = __ldg(di + lc);
-    di_l[s][1] = __ldg(di + lc + 1);  // beyond-the-edge values only ever meet zero ERI entries
-  }
-#pragma unroll
-  for (int t = 0; t < KC; ++t) {
-    const int k = k0 + t;
-    ok[t] = MODE == 0 || (k <= i && l0 <= k);
-    const int kc = k <= i ? k : i;
-    const double2 q2 = ok[t] ? __ldg(reinterpret_cast<const double2*>(dq2 + seg_off(kc) + lc))
-                             : make_double2(0.0, 0.0);
-    dq[t][0] = q2.x;
-    dq[t][1] = q2.y;
-#pragma unroll
-    for (int s = 0; s < NSPIN; ++s) di_k[s][t] = __ldg(D + s * dstride + (size_t)i * n + kc);
-  }
-  double a1[NSPIN][KC], a2[NSPIN][2], jq[KC][2];
-#pragma unroll
-  for (int t = 0; t < KC; ++t) {
-    jq[t][0] = jq[t][1] = 0.0;
-#pragma unroll
-    for (int s = 0; s < NSPIN; ++s) a1[s][t] = 0.0;
-  }
-#pragma unroll
-  for (int s = 0; s < NSPIN; ++s) a2[s][0] = a2[s][1] = 0.0;
-
-  const int rows = i + 1;
-  int jc = (int)(rot % (uint32_t)rows);  // same rotated row order as the producer
-  double* kj0 = Kp + (size_t)jc * n;
-  int parked = 0, j_tile = jc;
-  double dp2 = __ldg(dq2 + Ei + jc);
-
-  const int red_r = lane / NV, red_v = lane - red_r * NV;
-  auto flush_tile = [&](int n_rows) {
-    __syncwarp();
-    if (red_r < n_rows) {
-      const double2* src = reinterpret_cast<const double2*>(ys + lane * YS);
-      double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const double2 v = src[q];
-        acc0 += v.x;
-        acc1 += v.y;
-      }
-      const double tot = acc0 + acc1;
-      int jr = j_tile + red_r;
-      if (jr >= rows) jr -= rows;
-      if (red_v == NV - 1) {
-        atomicAdd(Jp + Ei + jr, tot);  // J~[pr(i,j)]
-      } else {
-        const int sp = red_v / KC, t = red_v - sp * KC;
-        if (MODE == 0 || k0 + t <= i) atomicAdd(Kp + sp * dstride + (size_t)jr * n + k0 + t, tot);  // K'[j,k]
-      }
-    }
-    __syncwarp();
-  };
-
-  for (int step = 0; step < rows; ++step) {
-    const int jn = jc + 1 == rows ? 0 : jc + 1;
-    const double dp2_next = __ldg(dq2 + Ei + jn);
-    const uint32_t slot = sc % DEPTH;
-    mbar_wait(full + slot, (sc / DEPTH) & 1);
-    const double* st = stages + slot * STG;
-    double2 w[KC];
-#pragma unroll
-    for (int t = 0; t < KC; ++t) {
-      const double2 v = reinterpret_cast<const double2*>(st + t * 64)[lane];
-      // bytes beyond the copied length are stale: select, never multiply
-      const bool valid = MODE == 0 ? true : (MODE == 2 ? (ok[t] && (k0 + t < i || l0 <= jc)) : ok[t]);
-      w[t] = valid ? v : make_double2(0.0, 0.0);
-    }
-    double dj_l[NSPIN][2], dj_k[NSPIN][KC];
-#pragma unroll
-    for (int s = 0; s < NSPIN; ++s) {
-      const double2 v = reinterpret_cast<const double2*>(st + KC * 64 + s * 64)[lane];
-      dj_l[s][0] = v.x;
-      dj_l[s][1] = v.y;
-      const double* dk = st + KC * 64 + NSPIN * 64 + s * KC;  // broadcast reads
-#pragma unroll
-      for (int t = 0; t < KC; t += 2) {
-        const double2 u = *reinterpret_cast<const double2*>(dk + t);
-        dj_k[s][t] = u.x;
-        dj_k[s][t + 1] = u.y;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty + slot);  // operands are in registers: hand the stage back
-    ++sc;
-
-    double jp0 = 0.0, jp1 = 0.0;
-    double z[NSPIN][2];
-#pragma unroll
-    for (int s = 0; s < NSPIN; ++s) z[s][0] = z[s][1] = 0.0;
-    double* park = ys + parked * NV * YS + lane;
-#pragma unroll
-    for (int t = 0; t < KC; ++t) {
-      const double w0 = w[t].x, w1 = w[t].y;
-      jp0 = fma(w0, dq[t][0], jp0);
-      jp1 = fma(w1, dq[t][1], jp1);
-      jq[t][0] = fma(w0, dp2, jq[t][0]);
-      jq[t][1] = fma(w1, dp2, jq[t][1]);
-#pragma unroll
-      for (int s = 0; s < NSPIN; ++s) {
-        a1[s][t] = fma(w0, dj_l[s][0], a1[s][t]);
-        a1[s][t] = fma(w1, dj_l[s][1], a1[s][t]);
-        a2[s][0] = fma(w0, dj_k[s][t], a2[s][0]);
-        a2[s][1] = fma(w1, dj_k[s][t], a2[s][1]);
-        park[(s * KC + t) * YS] = fma(w1, di_l[s][1], w0 * di_l[s][0]);  // -> K'[j,k]
-        z[s][0] = fma(w0, di_k[s][t], z[s][0]);
-        z[s][1] = fma(w1, di_k[s][t], z[s][1]);
-      }
-    }
-    park[(NV - 1) * YS] = jp0 + jp1;  // -> J~[pr(i,j)]
-#pragma unroll
-    for (int s = 0; s < NSPIN; ++s) {
-      double* kj = kj0 + s * dstride;
-      if (l0_in) atomicAdd(kj + l0, z[s][0]);  // K'[j,l]
-      if (l1_in) atomicAdd(kj + l0 + 1, z[s][1]);
-    }
-    if (++parked == RB) {
-      flush_tile(RB);
-      parked = 0;
-      j_tile = jn;
-    }
-    jc = jn;
-    kj0 = jn ? kj0 + n : Kp;
-    dp2 = dp2_next;
-  }
-  if (parked) flush_tile(parked);
-
-#pragma unroll
-  for (int s = 0; s < NSPIN; ++s) {
-    double* ki = Kp + s * dstride + (size_t)n * i;
-    if (l0_in) atomicAdd(ki + l0, a2[s][0]);  // K'[i,l]
-    if (l1_in) atomicAdd(ki + l0 + 1, a2[s][1]);
-    const double r = warp_transpose_reduce<KC>(a1[s], lane);
-    const int t = transpose_reduce_index<KC>(lane);
-    if (transpose_reduce_owner<KC>(lane) && k0 + t <= i) atomicAdd(ki + k0 + t, r);  // K'[i,k]
-  }
-#pragma unroll
-  for (int t = 0; t < KC; ++t)
-    if (ok[t]) {  // J~[q]
-      double* jo = Jp + seg_off(min(k0 + t, i)) + lc;
+    if (okA[t] || okB[t]) {  // J~[q]; the pad slot only ever receives zeros
+      double* jo = reinterpret_cast<double*>(reinterpret_cast<char*>(Jp) + off[t]);
       atomicAdd(jo, jq[t][0]);
       atomicAdd(jo + 1, jq[t][1]);
     }
 }
 
-// grid = one CTA per SM; block = 2 * WS_PAIRS warps (consumers first); dynamic smem = per-pair
-// [row-sum tile | DEPTH stages].
-template <int NSPIN, int KC>
-__global__ void __launch_bounds__(64 * WS_PAIRS, 1)
-jk_packed_ws_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Btab,
-                    uint64_t shard_offset, const double* __restrict__ D, size_t dstride,
-                    const double* __restrict__ dq2, double* __restrict__ Kp,
-                    double* __restrict__ Jp, int n, int i_lo, int i_hi, int* __restrict__ sched) {
-  extern __shared__ __align__(128) double ws_smem[];
-  __shared__ uint64_t full[WS_PAIRS][DEPTH], empty[WS_PAIRS][DEPTH];
-  __shared__ uint64_t item_full[WS_PAIRS][2], item_empty[WS_PAIRS][2];
-  __shared__ int item_q[WS_PAIRS][2];
-  constexpr int TILE = packed_rb(NSPIN, KC) * (NSPIN * KC + 1) * YS;
-  constexpr int STG = ws_stage_doubles(NSPIN, KC);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool producer = warp >= WS_PAIRS;
-  const int p = producer ? warp - WS_PAIRS : warp;
-  double* ys = ws_smem + (size_t)p * ws_pair_doubles(NSPIN, KC);
-  double* stages = ys + TILE;
-  const int per_i = ((n + KC - 1) / KC) * ((n + 63) / 64);
-  const int total = (i_hi - i_lo) * per_i;
-
-  if (threadIdx.x < WS_PAIRS) {
-    for (int d = 0; d < DEPTH; ++d) {
-      mbar_init(&full[threadIdx.x][d], 1);
-      mbar_init(&empty[threadIdx.x][d], 1);
-    }
-    for (int q = 0; q < 2; ++q) {
-      mbar_init(&item_full[threadIdx.x][q], 1);
-      mbar_init(&item_empty[threadIdx.x][q], 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (producer) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_PRODUCER_REGS));
-    // All 32 lanes stay converged and each owns at most ONE copy job of a row (lane t < KC: the
-    // k-segment k0+t; then per spin the D[j, l-window] piece and the D[j, k-chunk] piece): the
-    // address/length arithmetic runs once, SIMT-parallel, and only the UBLKCP issue itself is
-    // serialised over the active lanes (~8 instructions each) — a single posting lane needed
-    // ~450 instructions per row and was the bottleneck (6.25 ms).
-    static_assert(KC + 2 * NSPIN <= 32, "one copy job per producer lane");
-    uint32_t sc = 0;
-    for (int k = 0;; ++k) {
-      // draw the next valid item (lane 0 draws, everybody decodes)
-      int idx;
-      WsItem it;
-      it.valid = false;
-      do {
-        idx = lane == 0 ? atomicAdd(sched, 1) : 0;
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx < total) it = ws_decode<KC>(idx, n, i_hi);
-      } while (idx < total && !it.valid);
-      if (idx >= total) idx = -1;
-      if (lane == 0) {
-        if (k >= 2) mbar_wait(&item_empty[p][k & 1], ((k >> 1) & 1) ^ 1);
-        item_q[p][k & 1] = idx;
-        mbar_arrive(&item_full[p][k & 1]);  // release: the store above is visible to the waiter
-      }
-      __syncwarp();
-      if (idx < 0) break;
-
-      const int i = it.i, k0 = it.k0, wl = it.wl;
-      const int rows = i + 1;
-      const uint64_t Ei = seg_off(i);
-      const double* eri_i = eri + (Btab[i] - shard_offset);
-      const bool interior = k0 + KC - 1 < i && wl + 63 <= k0;  // MODE 0: every ERI copy is 512 bytes
-      int j = (int)(it.rot % (uint32_t)rows);
-      const double* row = eri_i + (uint64_t)j * Ei + seg_off(j);
-      // this lane's job: ERI segment (lane < KC) or a density piece
-      const int kk = k0 + lane;                       // segment index if lane < KC
-      const int q = lane - KC, sp = q >> 1;           // density job if 0 <= q < 2*NSPIN
-      const bool seg_job = lane < KC, dl_job = q >= 0 && q < 2 * NSPIN && !(q & 1),
-                 dk_job = q >= 0 && q < 2 * NSPIN && (q & 1);
-      const uint32_t soff = seg_job ? (uint32_t)seg_off(min(kk, i)) + (uint32_t)wl : 0u;
-      const int my_dst = seg_job ? lane * 64 : (dl_job ? KC * 64 + sp * 64 : KC * 64 + NSPIN * 64 + sp * KC);
-      const double* dsrc = D + (dl_job || dk_job ? sp * dstride : 0) + (dl_job ? wl : k0);  // + j*n per row
-      for (int step = 0; step < rows; ++step) {
-        const uint32_t slot = sc % DEPTH;
-        mbar_wait(&empty[p][slot], ((sc / DEPTH) & 1) ^ 1);
-        double* dst = stages + slot * STG + my_dst;
-        uint64_t* bar = &full[p][slot];
-        uint32_t bytes = 0;
-        const double* src = row + soff;
-        if (seg_job) {
-          uint32_t len = 64;
-          if (!interior) {
-            // stored (padded) length of segment kk of row (i,j), clipped to this warp's l window
-            int seg = kk > i ? 0 : ((kk < i ? kk : j) + 2) & ~1;
-            seg -= wl;
-            len = seg <= 0 ? 0u : (uint32_t)(seg < 64 ? seg : 64);
-          }
-          bytes = len * 8u;
-        } else if (dl_job || dk_job) {
-          src = dsrc + (size_t)j * n;
-          bytes = dl_job ? 512u : KC * 8u;
-        }
-        if (bytes) bulk_g2s(dst, src, bytes, bar);
-        const uint32_t all = __reduce_add_sync(0xffffffffu, bytes);
-        // the one arrival of the phase; copies that landed earlier are already accounted for
-        if (lane == 0) mbar_expect_tx(bar, all);
-        ++sc;
-        if (j + 1 == rows) {
-          j = 0;
-          row = eri_i;
-        } else {
-          row += Ei + ((j + 2) & ~1);
-          ++j;
-        }
-      }
-    }
-    return;
-  }
-
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_CONSUMER_REGS));
-  uint32_t sc = 0;
-  for (int k = 0;; ++k) {
-    mbar_wait(&item_full[p][k & 1], (k >> 1) & 1);
-    const int idx = item_q[p][k & 1];
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&item_empty[p][k & 1]);
-    if (idx < 0) break;
-    const WsItem it = ws_decode<KC>(idx, n, i_hi);
-    const int kmax = min(it.k0 + KC - 1, it.i);
-    if (kmax == it.i)
-      ws_consume_item<NSPIN, KC, 2>(D, dstride, dq2, Kp, Jp, ys, stages, full[p], empty[p], n, it.i, it.k0,
-                                    it.wl, lane, it.rot, sc);
-    else if (it.wl + 63 <= it.k0)
-      ws_consume_item<NSPIN, KC, 0>(D, dstride, dq2, Kp, Jp, ys, stages, full[p], empty[p], n, it.i, it.k0,
-                                    it.wl, lane, it.rot, sc);
+// Persistent: one CTA of WARPS independent warps per SM; every warp draws work items from a
+// global counter over a host-built list of the LIVE (pair, k-chunk, l-block) triples, heaviest
+// pair first and the l-blocks of one (pair, k-chunk) adjacent.  (One-warp CTAs launched per triple
+// left 20-35 % of the warp slots empty: dead triples beyond the triangle, block-launch latency and
+// warps that could not be placed on a sub-partition with enough free registers.)
+// item = pair << 16 | k-chunk << 6 | l-block; pair z covers iA = i_hi - 2 - 2z, iB = iA + 1; the
+// last pair of an odd-sized shard is the single index i_lo (stream A only).
+template <int NSPIN, int KC, int DEPTH, int WARPS, bool VECD>
+__global__ void __launch_bounds__(32 * WARPS, 1)
+jk_packed_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Btab,
+                 uint64_t shard_offset, const double* __restrict__ D, size_t dstride,
+                 const double* __restrict__ dq2, double* __restrict__ Kp, double* __restrict__ Jp,
+                 int n, int i_lo, int i_hi, const uint32_t* __restrict__ items, int n_items,
+                 int* __restrict__ sched) {
+  extern __shared__ __align__(16) double pk_smem[];
+  const int lane = threadIdx.x & 31;
+  double* sm = pk_smem + (threadIdx.x >> 5) * PkSmem<NSPIN, KC, DEPTH>::TOTAL;
+  for (;;) {
+    int idx = lane == 0 ? atomicAdd(sched, 1) : 0;
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (idx >= n_items) break;
+    const uint32_t it = __ldg(items + idx);
+    int iA = i_hi - 2 - 2 * (int)(it >> 16);
+    const bool has_b = iA >= i_lo;
+    if (!has_b) iA = i_lo;
+    const int iT = has_b ? iA + 1 : iA;
+    const int kc = (it >> 6) & 0x3ff, lb = it & 0x3f;
+    const int k0 = kc * KC;
+    const int wl = 64 * lb;  // first l of this warp
+    const int l0 = wl + 2 * lane;
+    const double* eri_a = eri + (Btab[iA] - shard_offset);
+    const double* eri_b = eri + (Btab[iT] - shard_offset);
+    const uint32_t rot = (uint32_t)kc * 40503u + (uint32_t)iA * 17u;
+    if (k0 + KC - 1 >= iA)
+      packed_item<NSPIN, KC, DEPTH, 2, VECD>(eri_a, eri_b, D, dstride, dq2, Kp, Jp, sm, n, iA, has_b, k0, l0, lane, rot);
+    else if (wl + 63 <= k0)
+      packed_item<NSPIN, KC, DEPTH, 0, VECD>(eri_a, eri_b, D, dstride, dq2, Kp, Jp, sm, n, iA, has_b, k0, l0, lane, rot);
     else
-      ws_consume_item<NSPIN, KC, 1>(D, dstride, dq2, Kp, Jp, ys, stages, full[p], empty[p], n, it.i, it.k0,
-                                    it.wl, lane, it.rot, sc);
+      packed_item<NSPIN, KC, DEPTH, 1, VECD>(eri_a, eri_b, D, dstride, dq2, Kp, Jp, sm, n, iA, has_b, k0, l0, lane, rot);
+    __syncwarp();
   }
 }
 
@@ -945,6 +633,80 @@ int scfb_packed_upload_table(scfb_handle_s* h) {
   return SCFB_OK;
 }
 
+// Live work items of this shard for k-chunk width kc_w, in the order the warps draw them.
+static int build_items(scfb_handle_s* h, int kc_w, int slot) {
+  std::vector<uint32_t> items;
+  const int n_pairs = (h->i_hi - h->i_lo + 1) / 2;
+  for (int z = 0; z < n_pairs; ++z) {
+    int iA = h->i_hi - 2 - 2 * z;
+    const bool has_b = iA >= h->i_lo;
+    if (!has_b) iA = h->i_lo;
+    const int iT = has_b ? iA + 1 : iA;
+    for (int kc = iT / kc_w; kc >= 0; --kc) {  // longest segments first
+      const int kmax = std::min(kc * kc_w + kc_w - 1, iT);
+      for (int lb = 0; 64 * lb <= kmax; ++lb) items.push_back((uint32_t)z << 16 | (uint32_t)kc << 6 | (uint32_t)lb);
+    }
+  }
+  h->pk_n_items[slot] = (int)items.size();
+  if (items.empty()) return SCFB_OK;
+  cudaError_t e = cudaMalloc(&h->pk_items[slot], items.size() * sizeof(uint32_t));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(h->pk_items[slot], items.data(), items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess)
+    return scfb_fail(h, e == cudaErrorMemoryAllocation ? SCFB_ERR_OOM : SCFB_ERR_CUDA, "packed item list: %s",
+                     cudaGetErrorString(e));
+  return SCFB_OK;
+}
+
+// One tuning point: k-chunk width, ring depth and warps per SM.  The register file is 16 K
+// registers per SM sub-partition: 255 registers per thread at 8 warps per SM, 168 at 12, 128 at 16.
+template <int NSPIN, int KC, int DEPTH, int WARPS, bool VECD>
+static int launch_packed_cfg(scfb_handle_s* h, double* Jp, double* Kp, size_t dstride, int slot) {
+  const size_t smem = (size_t)WARPS * PkSmem<NSPIN, KC, DEPTH>::TOTAL * sizeof(double);
+  auto kern = jk_packed_kernel<NSPIN, KC, DEPTH, WARPS, VECD>;
+  if (!h->pk_items[slot] && h->pk_n_items[slot] < 0) {  // first launch of this instantiation on this handle
+    if (int rc = build_items(h, KC, slot)) return rc;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "jk_packed_kernel attributes: %s", cudaGetErrorString(e));
+  }
+  if (h->n_sm == 0) {
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
+    if (h->n_sm <= 0) h->n_sm = 148;
+  }
+  const int n_items = h->pk_n_items[slot];
+  if (n_items == 0) return SCFB_OK;
+  cudaError_t e = cudaMemsetAsync(h->sched, 0, sizeof(int), h->stream);
+  if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+  const int grid = std::min(h->n_sm, (n_items + WARPS - 1) / WARPS);
+  kern<<<grid, 32 * WARPS, smem, h->stream>>>(h->eri, h->pk_btab, h->pk_offset, h->pk_dpad, dstride, h->pk_dq2,
+                                            Kp, Jp, h->n, h->i_lo, h->i_hi, h->pk_items[slot], n_items, h->sched);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "jk_packed_kernel launch: %s", cudaGetErrorString(e));
+  h->launches += 1;
+  return SCFB_OK;
+}
+
+template <int NSPIN, bool VECD>
+static int launch_packed(scfb_handle_s* h, double* Jp, double* Kp, size_t dstride) {
+  static const int variant = [] {  // EXPERIMENT knob, removed once the tuning point is chosen
+    const char* v = std::getenv("SCFB_PACKED_VARIANT");
+    return v ? std::atoi(v) : 0;
+  }();
+  const int slot = (NSPIN - 1) * 4 + (variant & 3);
+  if (NSPIN == 1) {
+    switch (variant) {
+      case 1: return launch_packed_cfg<1, 4, 3, 12, VECD>(h, Jp, Kp, dstride, slot);
+      case 2: return launch_packed_cfg<1, 4, 2, 12, VECD>(h, Jp, Kp, dstride, slot);
+      case 3: return launch_packed_cfg<1, 4, 2, 16, VECD>(h, Jp, Kp, dstride, slot);
+      default: return launch_packed_cfg<1, 8, 2, 8, VECD>(h, Jp, Kp, dstride, slot);
+    }
+  }
+  switch (variant) {
+    case 1: return launch_packed_cfg<2, 4, 2, 12, VECD>(h, Jp, Kp, dstride, slot);
+    default: return launch_packed_cfg<2, 4, 2, 8, VECD>(h, Jp, Kp, dstride, slot);
+  }
+}
+
 int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
                           const double* d_total) {
   const int n = h->n;
@@ -958,77 +720,15 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
   const size_t dstride = n2 + DPAD;
   h->launches += 1;
   if (h->timed) cudaEventRecord(h->ev[3], h->stream);
-  const int n_i = h->i_hi - h->i_lo;
-  if (n_i > 0) {
+  if (h->i_hi > h->i_lo) {
     double* Jp = h->pk_acc;
     double* Kp = h->pk_acc + PQ;
-    // SCFB_PACKED_TMA=1 selects the warp-specialised bulk-copy (v5) kernel (RHF, even n); read per
-    // launch so that one test process can cover both kernels
-    const char* tma_env = std::getenv("SCFB_PACKED_TMA");
-    const int use_tma = tma_env ? std::atoi(tma_env) : 0;
-    static const int minb_sel = [] {  // tuning knob: SCFB_PACKED_MINB=3|4 (CTAs per SM, KC=4 RHF)
-      const char* v = std::getenv("SCFB_PACKED_MINB");
-      return v ? std::atoi(v) : 4;
-    }();
-    static const int kc_sel = [] {  // tuning knob: SCFB_PACKED_KC=4|8
-      const char* v = std::getenv("SCFB_PACKED_KC");
-      return v ? std::atoi(v) : 0;
-    }();
-    const int kc = kc_sel == 4 || kc_sel == 8 ? kc_sel : 8;
-    if (use_tma && n % 2 == 0 && n_spin == 1 && kc == 8) {
-      if (h->n_sm == 0) {
-        cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
-        if (h->n_sm <= 0) h->n_sm = 148;
-      }
-      const int n_sm = h->n_sm;
-      const size_t sm_ = (size_t)WS_PAIRS * ws_pair_doubles(1, 8) * sizeof(double);
-      cudaFuncSetAttribute(jk_packed_ws_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_);
-      e = cudaMemsetAsync(h->sched, 0, sizeof(int), h->stream);
-      if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
-      jk_packed_ws_kernel<1, 8><<<n_sm, 64 * WS_PAIRS, sm_, h->stream>>>(
-          h->eri, h->pk_btab, h->pk_offset, h->pk_dpad, dstride, h->pk_dq2, Kp, Jp, n, h->i_lo, h->i_hi,
-          h->sched);
-      e = cudaGetLastError();
-      if (e != cudaSuccess)
-        return scfb_fail(h, SCFB_ERR_CUDA, "jk_packed_ws_kernel launch: %s", cudaGetErrorString(e));
-      h->launches += 1;
-      if (h->timed) cudaEventRecord(h->ev[1], h->stream);
-      unpack_jk_kernel<<<148 * 2, 256, 0, h->stream>>>(h->pk_acc, h->pk_acc + PQ, h->jk, n, n_spin);
-      e = cudaGetLastError();
-      if (e != cudaSuccess)
-        return scfb_fail(h, SCFB_ERR_CUDA, "unpack_jk_kernel launch: %s", cudaGetErrorString(e));
-      h->launches += 1;
-      return SCFB_OK;
-    }
-    dim3 grid((n + kc - 1) / kc, n_i, (n + 2 * LB - 1) / (2 * LB));
-#define SCFB_PK_LAUNCH(NS, KCV, MINB)                                                          \
-  do {                                                                                          \
-    const size_t sm_ = packed_smem_bytes(NS, KCV);                                              \
-    if (n % 2 == 0) {                                                                           \
-      cudaFuncSetAttribute(jk_packed_kernel<NS, KCV, MINB, true>,                               \
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_);              \
-      jk_packed_kernel<NS, KCV, MINB, true><<<grid, LB, sm_, h->stream>>>(                      \
-          h->eri, h->pk_btab, h->pk_offset, h->pk_dpad, dstride, h->pk_dq2, Kp, Jp, n, h->i_lo); \
-    } else {                                                                                    \
-      cudaFuncSetAttribute(jk_packed_kernel<NS, KCV, MINB, false>,                              \
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_);              \
-      jk_packed_kernel<NS, KCV, MINB, false><<<grid, LB, sm_, h->stream>>>(                     \
-          h->eri, h->pk_btab, h->pk_offset, h->pk_dpad, dstride, h->pk_dq2, Kp, Jp, n, h->i_lo); \
-    }                                                                                           \
-  } while (0)
-    // resident CTAs per SM targeted by __launch_bounds__ (register cap = 65536 / (LB * MINB))
-    constexpr int W = 128 / LB;  // CTAs per 128 threads
-    (void)minb_sel;
-    if (n_spin == 1 && kc == 8) SCFB_PK_LAUNCH(1, 8, 2 * W);
-    else if (n_spin == 1 && minb_sel == 4) SCFB_PK_LAUNCH(1, 4, 4 * W);
-    else if (n_spin == 1) SCFB_PK_LAUNCH(1, 4, 3 * W);
-    else if (kc == 8) SCFB_PK_LAUNCH(2, 8, 2 * W);
-    else SCFB_PK_LAUNCH(2, 4, 3 * W);
-#undef SCFB_PK_LAUNCH
-    e = cudaGetLastError();
-    if (e != cudaSuccess)
-      return scfb_fail(h, SCFB_ERR_CUDA, "jk_packed_kernel launch: %s", cudaGetErrorString(e));
-    h->launches += 1;
+    int rc;
+    if (n % 2 == 0)
+      rc = n_spin == 1 ? launch_packed<1, true>(h, Jp, Kp, dstride) : launch_packed<2, true>(h, Jp, Kp, dstride);
+    else
+      rc = n_spin == 1 ? launch_packed<1, false>(h, Jp, Kp, dstride) : launch_packed<2, false>(h, Jp, Kp, dstride);
+    if (rc) return rc;
   }
   if (h->timed) cudaEventRecord(h->ev[1], h->stream);
   unpack_jk_kernel<<<148 * 2, 256, 0, h->stream>>>(h->pk_acc, h->pk_acc + PQ, h->jk, n, n_spin);

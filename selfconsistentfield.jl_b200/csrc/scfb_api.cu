@@ -180,6 +180,7 @@ int scfb_destroy(scfb_handle_t h) {
   cudaFree(h->pk_dq2);
   cudaFree(h->pk_dpad);
   cudaFree(h->pk_btab);
+  for (auto* p : h->pk_items) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
