@@ -122,9 +122,16 @@ def random_symmetric_eri(n, rng):
     return np.asfortranarray(t / 8)
 
 
+PACKED8_SEG_PAD = 8          # every k-segment is zero-padded to a multiple of 8 elements (64 bytes)
+
+
+def packed8_seg_len(l_count):
+    return -(-l_count // PACKED8_SEG_PAD) * PACKED8_SEG_PAD
+
+
 def packed8_seg_off(k):
-    """Padded elements of the k-segments 0..k-1 of a packed row (each padded to even length)."""
-    return k * (k + 1) // 2 + (k + 1) // 2
+    """Padded elements of the k-segments 0..k-1 of a packed row."""
+    return sum(packed8_seg_len(m + 1) for m in range(k))
 
 
 def packed8_total(n):
@@ -134,8 +141,8 @@ def packed8_total(n):
 
 def pack8(eri, i_lo=0, i_hi=None):
     """Oracle statement of the packed8 storage: for i >= j the row (i,j) holds the
-    segments k = 0..i with l = 0..k (k < i) or l = 0..j (k == i), each padded with one zero to
-    even length; value (ij|kl) * 0.5^{[i=j]+[k=l]+[pr(i,j)=pr(k,l)]}."""
+    segments k = 0..i with l = 0..k (k < i) or l = 0..j (k == i), each zero-padded to a multiple
+    of 8 elements; value (ij|kl) * 0.5^{[i=j]+[k=l]+[pr(i,j)=pr(k,l)]}."""
     n = eri.shape[0]
     i_hi = n if i_hi is None else i_hi
     out = []
@@ -146,6 +153,5 @@ def pack8(eri, i_lo=0, i_hi=None):
                 for l in range(lmax + 1):
                     v = eri[i, j, k, l] * 0.5 ** ((i == j) + (k == l) + (i == k and j == l))
                     out.append(v)
-                if (lmax + 1) % 2:
-                    out.append(0.0)
+                out.extend([0.0] * (packed8_seg_len(lmax + 1) - (lmax + 1)))
     return np.array(out)

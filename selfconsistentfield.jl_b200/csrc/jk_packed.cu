@@ -2,11 +2,13 @@
 //
 // Storage (this library's own HBM layout, "packed8"): pair index pr(i,j) = i(i+1)/2 + j,
 // i >= j.  Row p = pr(i,j) holds the canonical elements (ij|kl) with pr(k,l) <= p, grouped
-// in k-segments (l = 0..k; the last segment k = i stops at l = j).  Every segment is padded
-// with one zero to EVEN length so that all segment and row starts are 16-byte aligned:
-//   E(k)   = k(k+1)/2 + (k+1)/2        padded elements of segments 0..k-1
+// in k-segments (l = 0..k; the last segment k = i stops at l = j).  Every segment is zero-padded
+// to a multiple of 8 elements so that all segment and row starts are 64-byte aligned — every
+// 512-byte run a warp reads then covers whole DRAM atoms (16-byte alignment made the stream
+// fetch 1.13-1.25x its bytes):
+//   E(k)   = sum_{m<k} ceil8(m+1)       padded elements of segments 0..k-1
 //   R(i,j) = B[i] + j*E(i) + E(j)      offset of row (i,j);  B[i+1] = B[i] + (i+1)E(i) + E(i+1)
-// (padding overhead ~0.5 % at n = 384; roofline figures use the UNPADDED byte count).
+// (padding overhead 2.4 % at n = 384; roofline figures use the UNPADDED byte count).
 // Stored value f = (ij|kl) * 0.5^{[i=j] + [k=l] + [p=q]} — exact power-of-two pre-scaling, so
 // that applying all 8 index permutations to every stored element gives each distinct tensor
 // element weight 1.  Valid only for 8-fold symmetric tensors and
@@ -47,7 +49,14 @@ namespace {
 constexpr int LB = 32;  // threads per CTA; 2*LB l values
 
 __host__ __device__ __forceinline__ uint64_t tri(uint64_t i) { return i * (i + 1) / 2; }
-__host__ __device__ __forceinline__ uint64_t seg_off(uint64_t k) { return tri(k) + (k + 1) / 2; }
+// every k-segment is padded with zeros to a multiple of SEG_PAD elements (64 bytes)
+constexpr uint64_t SEG_PAD = 8;
+__host__ __device__ __forceinline__ uint64_t seg_len(uint64_t l_count) { return (l_count + SEG_PAD - 1) & ~(SEG_PAD - 1); }
+// padded elements of the segments 0..k-1: sum_{m<k} seg_len(m+1) = 8 (q+1) (4q + r), k = 8q + r
+__host__ __device__ __forceinline__ uint64_t seg_off(uint64_t k) {
+  const uint64_t q = k / SEG_PAD, r = k % SEG_PAD;
+  return SEG_PAD * (q + 1) * (SEG_PAD / 2 * q + r);
+}
 
 // Sum V (4 or 8) per-lane values over the 32 lanes of a warp with V+1 (instead of 5V)
 // shuffles: each butterfly stage halves the number of values a lane still carries.
@@ -229,7 +238,7 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
 
   // ---- load side: row pair jl goes to the ring DEPTH-1 pairs ahead of its use (warp-uniform state) ----
   int jl = j_first;
-  // row (i,j+1) starts E(i) + ceil2(j+1) elements after row (i,j); stream A's pointer is only
+  // row (i,j+1) starts E(i) + seg_len(j+1) elements after row (i,j); stream A's pointer is only
   // dereferenced while jl <= iA
   const char* rowA = reinterpret_cast<const char*>(eri_a + (uint64_t)jl * EA + seg_off(jl));
   const char* rowB = reinterpret_cast<const char*>(eri_b + (uint64_t)jl * EB + seg_off(jl));
@@ -281,7 +290,7 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
       rowA = reinterpret_cast<const char*>(eri_a);
       rowB = reinterpret_cast<const char*>(eri_b);
     } else {
-      const uint32_t c2 = (uint32_t)((jl + 2) & ~1) * 8u;
+      const uint32_t c2 = (uint32_t)seg_len(jl + 1) * 8u;
       rowA += stepA + c2;
       rowB += stepB + c2;
       ++jl;
@@ -513,7 +522,7 @@ __global__ void pack_density_kernel(const double* __restrict__ dtot, const doubl
                                     int n_spin) {
   for (int k = blockIdx.x; k < n; k += gridDim.x) {
     const uint64_t base = seg_off(k);
-    const int len = (k + 2) & ~1;
+    const int len = (int)seg_len(k + 1);
     for (int l = threadIdx.x; l < len; l += blockDim.x)
       dq2[base + l] = l <= k ? 2.0 * dtot[k + (size_t)n * l] : 0.0;
     for (int s = 0; s < n_spin; ++s) {
@@ -563,7 +572,7 @@ __global__ void generate_packed_kernel(double* __restrict__ eri, const uint64_t*
     while (tri(i) > p) --i;
     const uint64_t j = p - tri(i);
     double* row = eri + (Btab[i] + j * seg_off(i) + seg_off(j) - shard_offset);
-    const uint64_t len = seg_off(i) + ((j + 2) & ~1ull);
+    const uint64_t len = seg_off(i) + seg_len(j + 1);
     uint64_t k = 0;  // segment containing the thread's position (walks forward only)
     for (uint64_t e = threadIdx.x; e < len; e += blockDim.x) {
       while (seg_off(k + 1) <= e) ++k;
@@ -769,7 +778,7 @@ void scfb_pack_host(const double* full, int n, int i_lo, int i_hi, double* out) 
           if (p == q) v *= 0.5;
           out[pos++] = v;
         }
-        if ((lmax + 1) & 1) out[pos++] = 0.0;  // pad the segment to even length
+        for (uint64_t l = lmax + 1; l < seg_len(lmax + 1); ++l) out[pos++] = 0.0;  // pad the segment
       }
     }
 }

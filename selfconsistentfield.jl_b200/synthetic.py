@@ -36,7 +36,7 @@ def hash_density(n: int, seed: int) -> np.ndarray:
 
 def packed8_total(n: int) -> int:
     """Stored (padded) elements of the packed8 layout (csrc/jk_packed.cu: B[n])."""
-    seg = lambda k: k * (k + 1) // 2 + (k + 1) // 2
+    seg = lambda k: 8 * (k // 8 + 1) * (4 * (k // 8) + k % 8)       # segments padded to 8 elements
     return sum((i + 1) * seg(i) + seg(i + 1) for i in range(n))
 
 
