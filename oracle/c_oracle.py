@@ -18,6 +18,8 @@ def lib():
             subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
         _lib = C.CDLL(_PATH)
         _lib.jk_literal_ld.argtypes = [_dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
+        _lib.jk_literal_ld_slabs.argtypes = [_dp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
+        _lib.jk_literal_ld_slabs.restype = None
         _lib.jk_onepass_omp.argtypes = [_dp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, _dp]
         _lib.hash_eri_slabs.argtypes = [_dp, C.c_int, C.c_uint64, C.c_int, C.c_int]
         _lib.chain_eri_slabs.argtypes = [_dp, C.c_int, _dp, C.c_int, C.c_int]
@@ -39,6 +41,20 @@ def jk_literal_ld(eri, density, total_density):
     j = np.zeros((n, n), order="F")
     k = np.zeros((n, n, n_spin), order="F")
     lib().jk_literal_ld(_p(e), n, n_spin, _p(d), _p(t), _p(j), _p(k))
+    return j, k
+
+
+def jk_literal_ld_slabs(eri_slabs, density, total_density):
+    """Columns J[:, nu_s] (n, S) and K[:, nu_s, spin] (n, S, n_spin) of the literal contraction for the
+    S nu-slabs in `eri_slabs` ((n,n,n,S), F-ordered), long-double accumulation."""
+    n, n_spin = density.shape[0], density.shape[2]
+    e = np.asfortranarray(eri_slabs, dtype=np.float64)
+    n_slabs = e.shape[3]
+    d = np.asfortranarray(density, dtype=np.float64)
+    t = np.asfortranarray(total_density, dtype=np.float64)
+    j = np.zeros((n, n_slabs), order="F")
+    k = np.zeros((n, n_slabs, n_spin), order="F")
+    lib().jk_literal_ld_slabs(_p(e), n, n_spin, n_slabs, _p(d), _p(t), _p(j), _p(k))
     return j, k
 
 

@@ -37,6 +37,32 @@ void jk_literal_ld(const double* eri, int n, int n_spin, const double* density, 
     }
 }
 
+/* The same literal contraction for a SAMPLE of nu-slabs: `eri_slabs` holds n_slabs slabs
+ * X[a,b,c] = eri[a,b,c,nu] back to back; column s of the outputs is J[:,nu_s] (n doubles) and
+ * K[:,nu_s,spin] ((n, n_slabs, n_spin) column-major).  J[m,nu] and K[m,nu] need only slab nu
+ * (JKBuilderFromTensor.jl:37: the last tensor index is the open index nu in both terms), which is
+ * what lets the tests check dense densities at sizes whose full tensor no host can hold. */
+void jk_literal_ld_slabs(const double* eri_slabs, int n, int n_spin, int n_slabs, const double* density,
+                         const double* dtot, double* Jcols, double* Kcols) {
+  const size_t N = (size_t)n;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int v = 0; v < n_slabs; ++v)
+    for (int m = 0; m < n; ++m) {
+      const double* X = eri_slabs + (size_t)v * N * N * N;
+      long double j = 0.0L, k0 = 0.0L, k1 = 0.0L;
+      for (size_t b = 0; b < N; ++b)
+        for (size_t a = 0; a < N; ++a) {
+          j += (long double)X[a + N * (b + N * m)] * (long double)dtot[a + N * b];
+          const long double x = (long double)X[m + N * (b + N * a)];
+          k0 += x * (long double)density[a + N * b];
+          if (n_spin == 2) k1 += x * (long double)density[a + N * b + N * N];
+        }
+      Jcols[m + N * v] = (double)j;
+      Kcols[m + N * v] = (double)k0;
+      if (n_spin == 2) Kcols[m + N * v + N * (size_t)n_slabs] = (double)k1;
+    }
+}
+
 /* One pass over nu-slabs [nu_lo, nu_hi) of a tensor stored slab-contiguously (`eri` points at
  * slab nu_lo): every element feeds J and every K.  fp64, one thread per slab. */
 void jk_onepass_omp(const double* eri, int n, int n_spin, const double* density, const double* dtot,

@@ -21,20 +21,22 @@
 //   K'[i,k] += f D[j,l]   K'[i,l] += f D[j,k]   K'[j,k] += f D[i,l]   K'[j,l] += f D[i,k]
 // and K = K' + K'^T.  2 + 4 n_spin FMAs per 8 bytes: still HBM-bound (1.5-2.5 flop/B).
 //
-// Mapping (details at `packed_item`): one warp = one CTA owns (i, chunk of KC consecutive
-// k <= i, 64 consecutive l); each lane owns an l-PAIR (16 bytes per k and row) and the warp loops
-// over the rows j = 0..i, each of which contributes contiguous runs of the packed row.
-//   * all per-row data (ERI pairs from HBM, the density row from L2) travels through a DEPTH-row
-//     cp.async (LDGSTS) ring in shared memory, DEPTH-1 rows ahead of its use; the row loop is
-//     unrolled DEPTH times so every ring and tile address is a compile-time offset;
+// Mapping (details at `packed_item`): one warp owns a work item (two consecutive first indices
+// iA, iA+1; a chunk of KC consecutive k; 64 consecutive l); each lane owns an l-PAIR (16 bytes per
+// k, row and stream) and the warp loops over the rows j, consuming row (iA,j) and row (iA+1,j)
+// together, each of which contributes contiguous 512-byte runs of the packed row.
+//   * all per-row data (ERI pairs from HBM, the density row from L2) travels through a DEPTH-deep
+//     cp.async (LDGSTS) ring in shared memory; the row loop is unrolled DEPTH times so every ring
+//     and tile address is a compile-time offset;
 //   * sums whose output does not depend on j (K'[i,k], K'[i,l], J~[q]) stay in registers for the
-//     whole item; K'[j,l] is lane-private (one RED per lane and row); the lane-reductions
-//     (K'[j,k], J~[p]) go through a conflict-free shared-memory tile flushed every DEPTH rows;
-//   * warps never synchronise with each other; cross-warp combination is fp64 RED.ADD into
-//     zeroed accumulators, so the packed path is deterministic only up to summation order
-//     (well inside the 1e-12 relative gate).
-// The l-blocks of one (i, k-chunk) are neighbours in launch order and walk the rows in the same
-// order, so the 64-byte DRAM atoms two neighbours share are fetched once (second one hits L2).
+//     whole item; K'[j,l] is lane-private (one RED per lane and row PAIR); the lane-reductions
+//     (K'[j,k], J~[p]) go through a conflict-free shared-memory tile flushed every DEPTH row pairs;
+//   * warps never synchronise with each other: a persistent CTA is 8 independent warps (one per
+//     SM sub-partition slot, 255 registers) that draw items from a global counter; cross-warp
+//     combination is fp64 RED.ADD into zeroed accumulators, so the packed path is deterministic
+//     only up to summation order (well inside the 1e-12 relative gate).
+// The l-blocks of one (pair, k-chunk) are neighbours in the item list and walk the rows in the same
+// order, so what two neighbours share of a DRAM page is fetched close in time.
 #include "scfb_internal.h"
 
 #include <algorithm>
@@ -42,11 +44,6 @@
 #include <vector>
 
 namespace {
-
-// One warp per CTA: the warps of an item never cooperate, and in the triangular iteration space
-// multi-warp CTAs keep dead warps' slots (and their shared memory) pinned until the longest
-// warp finishes; with one-warp CTAs every resident CTA is a live warp (measured 5.6 -> 4.9 ms).
-constexpr int LB = 32;  // threads per CTA; 2*LB l values
 
 __host__ __device__ __forceinline__ uint64_t tri(uint64_t i) { return i * (i + 1) / 2; }
 // every k-segment is padded with zeros to a multiple of SEG_PAD elements (64 bytes)
@@ -695,25 +692,13 @@ static int launch_packed_cfg(scfb_handle_s* h, double* Jp, double* Kp, size_t ds
   return SCFB_OK;
 }
 
+// Tuning points (same-box A/B at n_bf = 384, profiles/README.md): RHF KC = 8 at 8 warps per SM
+// (255 registers) beats KC = 4 at 12 or 16 warps; UHF needs KC = 4 to keep its 2x K state in
+// registers.
 template <int NSPIN, bool VECD>
 static int launch_packed(scfb_handle_s* h, double* Jp, double* Kp, size_t dstride) {
-  static const int variant = [] {  // EXPERIMENT knob, removed once the tuning point is chosen
-    const char* v = std::getenv("SCFB_PACKED_VARIANT");
-    return v ? std::atoi(v) : 0;
-  }();
-  const int slot = (NSPIN - 1) * 4 + (variant & 3);
-  if (NSPIN == 1) {
-    switch (variant) {
-      case 1: return launch_packed_cfg<1, 4, 3, 12, VECD>(h, Jp, Kp, dstride, slot);
-      case 2: return launch_packed_cfg<1, 4, 2, 12, VECD>(h, Jp, Kp, dstride, slot);
-      case 3: return launch_packed_cfg<1, 4, 2, 16, VECD>(h, Jp, Kp, dstride, slot);
-      default: return launch_packed_cfg<1, 8, 2, 8, VECD>(h, Jp, Kp, dstride, slot);
-    }
-  }
-  switch (variant) {
-    case 1: return launch_packed_cfg<2, 4, 2, 12, VECD>(h, Jp, Kp, dstride, slot);
-    default: return launch_packed_cfg<2, 4, 2, 8, VECD>(h, Jp, Kp, dstride, slot);
-  }
+  if (NSPIN == 1) return launch_packed_cfg<1, 8, 2, 8, VECD>(h, Jp, Kp, dstride, 0);
+  return launch_packed_cfg<2, 4, 2, 8, VECD>(h, Jp, Kp, dstride, 1);
 }
 
 int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,

@@ -41,8 +41,8 @@ struct scfb_handle_s {
   int* sched = nullptr;         // work-item counter of the persistent kernels
   int n_sm = 0;                 // SM count of this handle's device (lazily queried)
   bool tma_attr[3] = {false, false, false};  // per NSPIN: smem attributes of jk_full_tma_kernel set on this device
-  uint32_t* pk_items[8] = {};   // live work items of jk_packed_kernel, per instantiation (built at first launch)
-  int pk_n_items[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+  uint32_t* pk_items[2] = {};   // live work items of jk_packed_kernel per spin count (built at first launch)
+  int pk_n_items[2] = {-1, -1};
   int b_splits = 1;             // CTAs sharing one (nu, c-chunk) work item along b
   uint64_t kpart_elems = 0;
   double* h_stage = nullptr;    // pinned host staging, 5*n*n

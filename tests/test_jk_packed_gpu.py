@@ -71,25 +71,6 @@ def test_packed_equals_full_layout_on_hash_family(n, n_spin):
     assert rel_err(jp, jf) < RTOL and rel_err(kp, kf) < RTOL
 
 
-@pytest.mark.parametrize("n", [2, 8, 18, 40, 64, 130])
-def test_packed_tma_variant_matches_default_kernel(n, monkeypatch):
-    """SCFB_PACKED_TMA=1: the warp-specialised producer/consumer kernel (jk_packed_ws_kernel,
-    RHF, even n) must give what the default LDGSTS kernel gives (both sum with fp64 RED, so the
-    comparison is to 1e-12 relative, not bitwise) — interior, edge and diagonal work items,
-    partial bulk copies, more items than producer/consumer pairs."""
-    d = synth.hash_symmetric_matrix(n, synth.SEED_DA)
-    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, layout="packed8")
-    monkeypatch.delenv("SCFB_PACKED_TMA", raising=False)
-    j0, k0 = b.jk(d[:, :, None], 2 * d)
-    launches0 = b.launch_count
-    monkeypatch.setenv("SCFB_PACKED_TMA", "1")
-    for _ in range(2):                       # twice: the item counter is reset per launch
-        j1, k1 = b.jk(d[:, :, None], 2 * d)
-        assert rel_err(j1, j0) < RTOL and rel_err(k1, k0) < RTOL
-    assert b.launch_count > launches0
-    b.close()
-
-
 @pytest.mark.parametrize("n,n_ranks", [(12, 2), (20, 4), (9, 8)])
 def test_packed_shard_partials_sum_to_full(n, n_ranks):
     rng = np.random.default_rng(n + n_ranks)
