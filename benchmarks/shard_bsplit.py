@@ -17,7 +17,7 @@ def one(a):
     import scf_b200
     from scf_b200 import synthetic
     n, n_spin = a.n_bas, a.n_spin
-    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synthetic.SEED_ERI, rank=a.rank, n_ranks=a.ranks)
+    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synthetic.SEED_ERI, rank=a.rank, n_ranks=a.ranks, allow_partial=True)
     dev = torch.device("cuda:0")
     d = torch.from_numpy(np.stack([synthetic.hash_density(n, synthetic.SEED_DA + s)
                                    for s in range(n_spin)], axis=0)).to(dev).contiguous()

@@ -74,7 +74,8 @@ int scfb_eri_upload(scfb_handle_t h, const double* host_eri);
 /* Chunked variant, full layout: `host_slabs` holds nu_count consecutive nu-slabs starting
  * at global slab nu_first; slabs outside the shard are skipped. */
 int scfb_eri_upload_slabs(scfb_handle_t h, const double* host_slabs, int nu_first, int nu_count);
-/* Declare the shard complete after a sequence of partial scfb_eri_upload_slabs calls. */
+/* Declare the shard complete after a sequence of partial scfb_eri_upload_slabs calls.  The handle
+ * tracks which owned nu-slabs have arrived: SCFB_ERR_STATE if any is still missing. */
 int scfb_eri_mark_ready(scfb_handle_t h);
 /* Fill the shard on the device from a closed-form synthetic family ("synthetic
  * inputs").  `aux` is family specific: HASH ignores it (may be NULL); CHAIN expects
@@ -93,6 +94,11 @@ int scfb_eri_download(scfb_handle_t h, double* host_shard);
  * returns the full result. */
 int scfb_fock_jk(scfb_handle_t h, int n_spin, const double* density,
                  const double* total_density, double* out);
+/* A handle created with n_ranks > 1 refuses to build (SCFB_ERR_STATE) until a cross-GPU exchange
+ * is set up (scfb_comm_init or scfb_peer_import): without one the result would silently be this
+ * rank's partial only.  scfb_allow_partial(h, 1) opts in to exactly that — the owned nu-columns
+ * (full layout) or this shard's dense partial sums (packed8) — for shard tests and timing. */
+int scfb_allow_partial(scfb_handle_t h, int allow);
 /* Same with DEVICE pointers, asynchronous on the handle's stream.  d_density and
  * d_total_density must be 16-byte aligned (SCFB_ERR_ARG otherwise). */
 int scfb_fock_jk_dev(scfb_handle_t h, int n_spin, const double* d_density,

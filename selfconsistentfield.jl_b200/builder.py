@@ -36,7 +36,7 @@ class JKBuilderCUDA(TwoElectronBuilder):
     rank,n_ranks  nu-slab shard owned by this builder (one builder per GPU/process)
     """
 
-    def __init__(self, n_bas, layout="full", device=0, rank=0, n_ranks=1):
+    def __init__(self, n_bas, layout="full", device=0, rank=0, n_ranks=1, allow_partial=False):
         self._h = capi._h()
         self.n_bas = int(n_bas)
         self.layout = layout
@@ -44,6 +44,8 @@ class JKBuilderCUDA(TwoElectronBuilder):
         self.rank, self.n_ranks = rank, n_ranks
         lay = {"full": capi.LAYOUT_FULL, "packed8": capi.LAYOUT_PACKED8}[layout]
         capi.check(capi.lib().scfb_create(C.byref(self._h), self.n_bas, lay, device, rank, n_ranks))
+        if allow_partial:
+            self.allow_partial()
 
     # ---- constructors -------------------------------------------------------------
     @classmethod
@@ -179,6 +181,11 @@ class JKBuilderCUDA(TwoElectronBuilder):
     def peer_import(self, all_handles: bytes):
         assert len(all_handles) == 128 * self.n_ranks
         capi.check(capi.lib().scfb_peer_import(self._h, all_handles), self._h)
+
+    def allow_partial(self, allow=True):
+        """A rank of a multi-rank builder without an exchange refuses to build (its result would be
+        this rank's partial only); this opts in to exactly that (shard tests / shard timing)."""
+        capi.check(capi.lib().scfb_allow_partial(self._h, int(bool(allow))), self._h)
 
     def comm_init(self, id128: bytes):
         capi.check(capi.lib().scfb_comm_init(self._h, id128), self._h)

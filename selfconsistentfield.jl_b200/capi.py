@@ -46,6 +46,7 @@ _SIGNATURES = {
     "scfb_eri_mark_ready": [_h],
     "scfb_eri_generate": [_h, C.c_int, C.c_uint64, _dp],
     "scfb_eri_download": [_h, _dp],
+    "scfb_allow_partial": [_h, C.c_int],
     "scfb_fock_jk": [_h, C.c_int, _dp, _dp, _dp],
     "scfb_fock_jk_dev": [_h, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
     "scfb_jk_split": [_h, C.c_int, _dp, _dp, _dp, _dp],

@@ -311,7 +311,7 @@ int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core,
   }
   SCFB_CUDA(h, cudaMemcpyAsync(st->S, overlap, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   SCFB_CUDA(h, cudaMemcpyAsync(st->H, h_core, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (int rc_ = scfb_stream_sync_checked(h)) return rc_;
   return SCFB_OK;
 }
 
@@ -330,7 +330,7 @@ int scfb_scf_set_density(scfb_handle_t h, int n_spin, const double* density) {
   const size_t n2 = (size_t)st->n * st->n;
   SCFB_CUDA(h, cudaMemcpyAsync(st->D, density, n2 * n_spin * sizeof(double), cudaMemcpyHostToDevice,
                                h->stream));
-  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (int rc_ = scfb_stream_sync_checked(h)) return rc_;
   st->have_density = true;
   return SCFB_OK;
 }
@@ -342,7 +342,7 @@ int scfb_scf_set_fock(scfb_handle_t h, int n_spin, const double* fock) {
   const size_t n2 = (size_t)st->n * st->n;
   SCFB_CUDA(h, cudaMemcpyAsync(st->F, fock, n2 * n_spin * sizeof(double), cudaMemcpyHostToDevice,
                                h->stream));
-  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (int rc_ = scfb_stream_sync_checked(h)) return rc_;
   st->have_fock = true;
   return SCFB_OK;
 }
@@ -379,7 +379,7 @@ int scfb_scf_fock(scfb_handle_t h, double* energies4, double* error_norm) {
   SCFB_CUDA(h, cudaGetLastError());
   SCFB_CUDA(h, cudaMemcpyAsync(st->h_scal, st->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost,
                                h->stream));
-  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (int rc_ = scfb_stream_sync_checked(h)) return rc_;
   const double* v = st->h_scal;
   const double e1 = v[0];
   const double e2 = ns == 1 ? v[1] : 0.5 * (v[1] + v[2]);  // compute_fock_matrix.jl:44-53
@@ -420,7 +420,7 @@ int scfb_scf_roothaan(scfb_handle_t h) {
   }
   int info = 0;
   SCFB_CUDA(h, cudaMemcpyAsync(&info, st->dev_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (int rc_ = scfb_stream_sync_checked(h)) return rc_;
   if (info != 0) return scfb_fail(h, SCFB_ERR_CUSOLVER, "Dsygvd failed: info=%d", info);
   // D_s = C[:, 1:n_elec[s], s'] C[...]'   (compute_density.jl:16-32)
   for (int s = 0; s < ns; ++s) {
@@ -479,7 +479,7 @@ int scfb_scf_diis_push(scfb_handle_t h, int spin, int* m_out, double* row_cdiis,
   SCFB_CUDA(h, cudaGetLastError());
   SCFB_CUDA(h, cudaMemcpyAsync(st->h_scal, st->scal, 2 * kMaxPairs * sizeof(double),
                                cudaMemcpyDeviceToHost, h->stream));
-  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (int rc_ = scfb_stream_sync_checked(h)) return rc_;
   if (m_out) *m_out = m;
   for (int j = 0; j < m; ++j) {
     if (row_cdiis) row_cdiis[j] = st->h_scal[j];
@@ -512,7 +512,7 @@ int scfb_scf_diis_extrapolate(scfb_handle_t h, int spin, int m, const double* c)
   lincomb_kernel<<<blocks_for(n2), 256, 0, h->stream>>>(lc, st->coef, st->F + spin * n2, n2);
   h->launches += 1;
   SCFB_CUDA(h, cudaGetLastError());
-  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));  // h_scal staging is reused by the next call
+  if (int rc_ = scfb_stream_sync_checked(h)) return rc_;  // h_scal staging is reused by the next call
   st->have_fock = true;
   return SCFB_OK;
 }
@@ -566,7 +566,7 @@ int scfb_scf_get(scfb_handle_t h, int what, double* host_out) {
     default: return scfb_fail(h, SCFB_ERR_ARG, "unknown quantity %d", what);
   }
   SCFB_CUDA(h, cudaMemcpyAsync(host_out, src, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (int rc_ = scfb_stream_sync_checked(h)) return rc_;
   return SCFB_OK;
 }
 

@@ -296,9 +296,11 @@ __global__ void __launch_bounds__(MAX_THREADS + 32 * TMA_PRODUCERS, 2)
 jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dtot,
                    const double* __restrict__ dens, double* __restrict__ jk,
                    double* __restrict__ kpart, double* __restrict__ jpart, int n, int nu_lo, int R,
-                   int G, int S, int n_chunks, int n_slabs, int BS, int* __restrict__ sched) {
+                   int G, int S, int n_chunks, int n_slabs, int BS, int* __restrict__ sched,
+                   int* __restrict__ slab_done, unsigned int* __restrict__ grid_done, ScfbFuse fuse) {
   extern __shared__ __align__(128) double ring[];  // [S][stage]
   __shared__ double jred[MAX_THREADS / 32][TC];
+  __shared__ int slab_last;
   __shared__ uint64_t full[TMA_MAX_STAGES], empty[TMA_MAX_STAGES];
   // Work items are handed out dynamically (SMs do not all stream at the same rate: a static
   // round-robin was 6 % slower than one CTA per item).  Lane 0 of producer warp 0 draws the CTA's
@@ -575,6 +577,62 @@ jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dt
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
     if (lane == 0) mbar_arrive(empty + last_slot);
+
+    // ---- fused tail: the CTA that completes a nu-slab reduces it, accumulates / ships it ----
+    // (the producers are already streaming the next item; "last block" pattern: every writer
+    // fences, one thread counts, the CTA that sees the last count reads the partials back from L2)
+    if (BS == 1) {
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
+      if (tid == 0) {
+        const int last = atomicAdd(slab_done + slab, 1) == n_chunks - 1;
+        if (last) slab_done[slab] = 0;  // ready for the next build
+        slab_last = last;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
+      if (slab_last) {
+        __threadfence();
+        const size_t col = (size_t)(nu_lo + slab) * n;
+        const size_t stride = (size_t)NSPIN * n;
+        for (int i = tid; i < NSPIN * n; i += MAX_THREADS) {
+          const int sp = i >= n ? 1 : 0, a = i - sp * n;
+          const double* p = kpart + (size_t)slab * n_chunks * stride + i;
+          double v = 0.0;
+          int c = 0;
+          for (; c + 8 <= n_chunks; c += 8) {  // eight loads in flight, added in the same fixed order
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = __ldcg(p + (size_t)(c + u) * stride);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v += t[u];
+          }
+          for (; c < n_chunks; ++c) v += __ldcg(p + (size_t)c * stride);
+          const double jv = __ldcg(jk + col + a);  // J[a, nu]: written by this slab's items
+          jk[(size_t)(1 + sp) * n2 + col + a] = v;
+          if (fuse.out) fuse.out[(size_t)sp * n2 + col + a] += jv - v;
+          for (int r = 0; r < fuse.n_peers; ++r) {  // plain stores into every rank's landing zone (NVLink)
+            fuse.peer_jk[r][(size_t)(1 + sp) * n2 + col + a] = v;
+            if (sp == 0) fuse.peer_jk[r][col + a] = jv;
+          }
+        }
+        if (fuse.n_peers) __threadfence_system();
+      }
+    }
+  }
+
+  // ---- kernel tail: the last CTA re-arms the counters and publishes this rank's epoch ----
+  asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(grid_done, 1u) == gridDim.x - 1) {  // every CTA has drawn its last item and fenced its stores
+      *grid_done = 0;
+      *sched = 0;
+      if (fuse.n_peers) {
+        __threadfence_system();
+        for (int r = 0; r < fuse.n_peers; ++r) *reinterpret_cast<volatile unsigned long long*>(fuse.peer_flag[r]) = fuse.epoch;
+        __threadfence_system();
+      }
+    }
   }
 }
 
@@ -625,7 +683,7 @@ __global__ void accumulate_kernel(const double* __restrict__ jk, double* __restr
 }
 
 template <int NSPIN>
-cudaError_t launch_tma(scfb_handle_s* h, const double* d_density, const double* d_total) {
+cudaError_t launch_tma(scfb_handle_s* h, const double* d_density, const double* d_total, const ScfbFuse& fuse) {
   const int n = h->n;
   const int n_slabs = h->nu_hi - h->nu_lo;
   const int n_chunks = (n + TC - 1) / TC;
@@ -668,11 +726,10 @@ cudaError_t launch_tma(scfb_handle_s* h, const double* d_density, const double* 
   }();
   const long cap = per_sm > 0 ? (long)per_sm * n_sm : items;
   const int grid = (int)(items < cap ? items : cap);
-  cudaError_t e = cudaMemsetAsync(h->sched, 0, sizeof(int), h->stream);
-  if (e != cudaSuccess) return e;
+  // (the work-item counter and the completion counters are re-armed by the kernel's last CTA)
   jk_full_tma_kernel<NSPIN><<<grid, MAX_THREADS + 32 * TMA_PRODUCERS, smem, h->stream>>>(
       h->eri, d_total, d_density, h->jk, h->kpart, h->jpart, n, h->nu_lo, R, G, S, n_chunks, n_slabs,
-      h->b_splits, h->sched);
+      h->b_splits, h->sched, h->slab_done, h->grid_done, fuse);
   return cudaGetLastError();
 }
 
@@ -730,10 +787,14 @@ uint64_t scfb_jpart_elems_full(int n, int n_slabs) {
   return (uint64_t)n_slabs * n_chunks * scfb_full_b_splits(n, n_slabs) * TC;
 }
 
+// `fuse` (may be null): what the TMA kernel's slab finisher should do beyond filling h->jk;
+// *fused tells the caller whether it was honoured (TMA path, unsplit items) — otherwise the caller
+// runs the separate accumulate / push launches.
 int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
-                        const double* d_total) {
+                        const double* d_total, const ScfbFuse* fuse, bool* fused) {
   const int n = h->n;
   const int n_slabs = h->nu_hi - h->nu_lo;
+  if (fused) *fused = false;
   if (n_slabs <= 0) {  // this rank owns nothing: its partial stays zero
     if (h->timed) cudaEventRecord(h->ev[3], h->stream);
     if (h->timed) cudaEventRecord(h->ev[1], h->stream);
@@ -745,8 +806,16 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
   cudaError_t e;
   if (h->timed) cudaEventRecord(h->ev[3], h->stream);
   const bool wide = (even ? n / 2 : n) > MAX_THREADS;  // rows longer than one 256-thread pass
-  if (tma_path(n))  // SCFB_FULL_TMA=0 selects the register-prefetch (LDG) kernel
-    e = n_spin == 1 ? launch_tma<1>(h, d_density, d_total) : launch_tma<2>(h, d_density, d_total);
+  const bool tma = tma_path(n);  // SCFB_FULL_TMA=0 selects the register-prefetch (LDG) kernel
+  const bool in_kernel_tail = tma && h->b_splits == 1;
+  if (tma) {
+    ScfbFuse f{};
+    if (fuse && in_kernel_tail) {
+      f = *fuse;
+      if (fused) *fused = true;
+    }
+    e = n_spin == 1 ? launch_tma<1>(h, d_density, d_total, f) : launch_tma<2>(h, d_density, d_total, f);
+  }
   else if (even && !wide)
     e = n_spin == 1 ? launch_stream<2, 1, 256>(h, d_density, d_total)
                     : launch_stream<2, 2, 256>(h, d_density, d_total);
@@ -762,6 +831,10 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
   if (e != cudaSuccess)
     return scfb_fail(h, SCFB_ERR_CUDA, "jk_full_stream_kernel launch: %s", cudaGetErrorString(e));
   if (h->timed) cudaEventRecord(h->ev[1], h->stream);
+  if (in_kernel_tail) {  // K rows were reduced by the slab finishers
+    h->launches += 1;
+    return SCFB_OK;
+  }
   const int n_chunks = (n + TC - 1) / TC;
   const size_t total = (size_t)n * n_slabs * n_spin;
   int blocks = (int)((total + 255) / 256);

@@ -31,29 +31,34 @@ bool is_pinned(const void* p) {
 
 // Push the caller's host arrays to the device staging block [density 2n^2 | total n^2 | out 2n^2].
 // Page-locked caller buffers are copied straight from where they are; pageable ones go through
-// the handle's pinned staging buffer (one memcpy + one H2D copy).
+// the handle's pinned staging buffer (one memcpy + one H2D copy).  density / total_density travel on
+// the build stream (the stream kernel needs them); `out` — only needed by the final accumulate —
+// travels on the handle's side stream so that its PCIe time hides behind the ERI stream.
 int stage_inputs(scfb_handle_s* h, int n_spin, const double* density, const double* total,
                  const double* out) {
   const size_t n2 = (size_t)h->n * h->n;
-  if (is_pinned(density) && is_pinned(total) && (!out || is_pinned(out))) {
-    SCFB_CUDA(h, cudaMemcpyAsync(h->d_density, density, n2 * n_spin * sizeof(double),
-                                 cudaMemcpyHostToDevice, h->stream));
-    SCFB_CUDA(h, cudaMemcpyAsync(h->d_total, total, n2 * sizeof(double), cudaMemcpyHostToDevice,
-                                 h->stream));
-    if (out)
-      SCFB_CUDA(h, cudaMemcpyAsync(h->d_out, out, n2 * n_spin * sizeof(double),
-                                   cudaMemcpyHostToDevice, h->stream));
-    return SCFB_OK;
+  const bool pinned = is_pinned(density) && is_pinned(total) && (!out || is_pinned(out));
+  const double* src_d = density;
+  const double* src_t = total;
+  const double* src_o = out;
+  if (!pinned) {
+    std::memcpy(h->h_stage, density, n2 * n_spin * sizeof(double));
+    std::memcpy(h->h_stage + 2 * n2, total, n2 * sizeof(double));
+    if (out) std::memcpy(h->h_stage + 3 * n2, out, n2 * n_spin * sizeof(double));
+    src_d = h->h_stage;
+    src_t = h->h_stage + 2 * n2;
+    src_o = h->h_stage + 3 * n2;
   }
-  std::memcpy(h->h_stage, density, n2 * n_spin * sizeof(double));
-  std::memcpy(h->h_stage + 2 * n2, total, n2 * sizeof(double));
-  size_t count = 3 * n2;
   if (out) {
-    std::memcpy(h->h_stage + 3 * n2, out, n2 * n_spin * sizeof(double));
-    count = 3 * n2 + n2 * n_spin;
+    // the side stream may only overwrite d_out once the previous build's reads of it are done
+    SCFB_CUDA(h, cudaEventRecord(h->ev_side[0], h->stream));
+    SCFB_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_side[0], 0));
+    SCFB_CUDA(h, cudaMemcpyAsync(h->d_out, src_o, n2 * n_spin * sizeof(double), cudaMemcpyHostToDevice, h->side));
+    SCFB_CUDA(h, cudaEventRecord(h->ev_side[1], h->side));
   }
-  SCFB_CUDA(h, cudaMemcpyAsync(h->d_density, h->h_stage, count * sizeof(double),
-                               cudaMemcpyHostToDevice, h->stream));
+  SCFB_CUDA(h, cudaMemcpyAsync(h->d_density, src_d, n2 * n_spin * sizeof(double), cudaMemcpyHostToDevice,
+                               h->stream));
+  SCFB_CUDA(h, cudaMemcpyAsync(h->d_total, src_t, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   return SCFB_OK;
 }
 
@@ -61,12 +66,49 @@ int check_build_args(scfb_handle_s* h, int n_spin, const void* a, const void* b,
   SCFB_REQUIRE(h, n_spin == 1 || n_spin == 2, "n_spin must be 1 or 2 (got %d)", n_spin);
   SCFB_REQUIRE(h, a && b && c, "null array pointer");
   if (!h->eri_ready) return scfb_fail(h, SCFB_ERR_STATE, "ERI not loaded: call scfb_eri_upload/_generate first");
+  if (h->n_ranks > 1 && !h->nccl_comm && !scfb_peer_ready(h) && !h->allow_partial)
+    return scfb_fail(h, SCFB_ERR_STATE,
+                     "rank %d of %d has no cross-GPU exchange (scfb_comm_init / scfb_peer_import): the result "
+                     "would be this rank's partial only; scfb_allow_partial(h, 1) opts in to that",
+                     h->rank, h->n_ranks);
   return SCFB_OK;
 }
 
-int launch_jk(scfb_handle_s* h, int n_spin, const double* d_density, const double* d_total) {
-  return h->layout == SCFB_LAYOUT_FULL ? scfb_launch_jk_full(h, n_spin, d_density, d_total)
-                                       : scfb_launch_jk_packed(h, n_spin, d_density, d_total);
+// One Fock build on the handle's stream: the J/K kernels of this rank's shard, the cross-GPU
+// exchange when there is one, and (d_out != nullptr) out += J - K_s.  *jk_final = where the complete
+// [J | K_a | K_b] lives afterwards.  `out_event`: d_out becomes valid only once this event (recorded on
+// another stream) has fired — waited for right before the first kernel that touches d_out, and it
+// rules out accumulating inside the stream kernel.
+int build_jk(scfb_handle_s* h, int n_spin, const double* d_density, const double* d_total, double* d_out,
+             cudaEvent_t out_event, const double** jk_final) {
+  const bool use_peer = h->n_ranks > 1 && scfb_peer_ready(h);
+  const bool use_nccl = h->n_ranks > 1 && !use_peer && h->nccl_comm;
+  ScfbFuse fuse{};
+  if (use_peer)
+    scfb_peer_begin(h, &fuse);
+  else if (!use_nccl && !out_event)
+    fuse.out = d_out;  // single rank: the slab finishers accumulate, no further launch
+  bool fused = false;
+  if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+  if (int rc = h->layout == SCFB_LAYOUT_FULL ? scfb_launch_jk_full(h, n_spin, d_density, d_total, &fuse, &fused)
+                                             : scfb_launch_jk_packed(h, n_spin, d_density, d_total))
+    return rc;
+  if (out_event) SCFB_CUDA(h, cudaStreamWaitEvent(h->stream, out_event, 0));
+  const double* jk = h->jk;
+  if (use_peer) {
+    if (int rc = scfb_peer_exchange(h, n_spin, d_out, fused)) return rc;
+    jk = h->jk_sum;  // (valid when d_out == nullptr)
+  } else {
+    if (use_nccl) {
+      if (int rc = scfb_comm_allreduce_jk(h, n_spin)) return rc;
+      jk = h->jk_sum;
+    }
+    if (d_out && !(fused && fuse.out))
+      if (int rc = scfb_launch_accumulate(h, n_spin, jk, d_out)) return rc;
+  }
+  if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+  if (jk_final) *jk_final = jk;
+  return SCFB_OK;
 }
 
 }  // namespace
@@ -131,6 +173,8 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
   CREATE_CUDA(cudaSetDevice(device));
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) CREATE_CUDA(cudaEventCreate(&ev));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  for (auto& ev : h->ev_side) CREATE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   h->timed = true;
   if (h->eri_elems) CREATE_CUDA(cudaMalloc(&h->eri, h->eri_elems * sizeof(double)));
   CREATE_CUDA(cudaMalloc(&h->d_density, 5 * n2 * sizeof(double)));
@@ -143,7 +187,13 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
   if (h->kpart_elems) CREATE_CUDA(cudaMalloc(&h->kpart, h->kpart_elems * sizeof(double)));
   if (layout == SCFB_LAYOUT_FULL && h->b_splits > 1)
     CREATE_CUDA(cudaMalloc(&h->jpart, scfb_jpart_elems_full(n_bas, h->nu_hi - h->nu_lo) * sizeof(double)));
-  CREATE_CUDA(cudaMalloc(&h->sched, sizeof(int)));
+  CREATE_CUDA(cudaMalloc(&h->sched, 2 * sizeof(int)));  // [work-item counter | finished-CTA counter]
+  CREATE_CUDA(cudaMemsetAsync(h->sched, 0, 2 * sizeof(int), h->stream));
+  h->grid_done = reinterpret_cast<unsigned int*>(h->sched + 1);
+  if (layout == SCFB_LAYOUT_FULL && h->nu_hi > h->nu_lo) {
+    CREATE_CUDA(cudaMalloc(&h->slab_done, (h->nu_hi - h->nu_lo) * sizeof(int)));
+    CREATE_CUDA(cudaMemsetAsync(h->slab_done, 0, (h->nu_hi - h->nu_lo) * sizeof(int), h->stream));
+  }
   if (layout == SCFB_LAYOUT_PACKED8) {
     const uint64_t PQ = scfb_packed_dq_elems(n_bas);
     CREATE_CUDA(cudaMalloc(&h->pk_acc, (PQ + 2 * (n2 + 64)) * sizeof(double)));
@@ -176,14 +226,19 @@ int scfb_destroy(scfb_handle_t h) {
   cudaFree(h->kpart);
   cudaFree(h->jpart);
   cudaFree(h->sched);
+  cudaFree(h->slab_done);
   cudaFree(h->pk_acc);
   cudaFree(h->pk_dq2);
   cudaFree(h->pk_dpad);
   cudaFree(h->pk_btab);
   for (auto* p : h->pk_items) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
+  std::free(h->slab_seen);
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& ev : h->ev_side)
+    if (ev) cudaEventDestroy(ev);
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return SCFB_OK;
@@ -227,12 +282,17 @@ int scfb_eri_upload_slabs(scfb_handle_t h, const double* host_slabs, int nu_firs
   const int lo = nu_first > h->nu_lo ? nu_first : h->nu_lo;
   const int hi = nu_first + nu_count < h->nu_hi ? nu_first + nu_count : h->nu_hi;
   if (hi > lo) {
+    if (!h->slab_seen) {
+      h->slab_seen = static_cast<uint64_t*>(std::calloc((h->n + 63) / 64, sizeof(uint64_t)));
+      if (!h->slab_seen) return scfb_fail(h, SCFB_ERR_OOM, "host allocation failed");
+    }
     const uint64_t n3 = (uint64_t)h->n * h->n * h->n;
     SCFB_CUDA(h, cudaMemcpyAsync(h->eri + (uint64_t)(lo - h->nu_lo) * n3,
                                  host_slabs + (uint64_t)(lo - nu_first) * n3,
                                  (uint64_t)(hi - lo) * n3 * sizeof(double), cudaMemcpyHostToDevice,
                                  h->stream));
     SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int v = lo; v < hi; ++v) h->slab_seen[v >> 6] |= 1ull << (v & 63);
   }
   if (lo <= h->nu_lo && hi >= h->nu_hi) h->eri_ready = true;  // whole shard arrived in one call
   return SCFB_OK;
@@ -262,7 +322,21 @@ int scfb_eri_upload(scfb_handle_t h, const double* host_eri) {
 
 int scfb_eri_mark_ready(scfb_handle_t h) {  // after a sequence of partial slab uploads
   if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  if (h->eri_ready) return SCFB_OK;
+  if (h->layout == SCFB_LAYOUT_FULL)
+    for (int v = h->nu_lo; v < h->nu_hi; ++v)
+      if (!h->slab_seen || !(h->slab_seen[v >> 6] >> (v & 63) & 1))
+        return scfb_fail(h, SCFB_ERR_STATE, "nu-slab %d of the shard [%d, %d) was never uploaded", v, h->nu_lo,
+                         h->nu_hi);
+  if (h->layout == SCFB_LAYOUT_PACKED8 && h->eri_elems && !h->pk_rows_seen_all)
+    return scfb_fail(h, SCFB_ERR_STATE, "packed shard incomplete: not every owned row block was streamed in");
   h->eri_ready = true;
+  return SCFB_OK;
+}
+
+int scfb_allow_partial(scfb_handle_t h, int allow) {
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  h->allow_partial = allow != 0;
   return SCFB_OK;
 }
 
@@ -307,21 +381,7 @@ int scfb_fock_jk_dev(scfb_handle_t h, int n_spin, const double* d_density,
   // pointer would fault on the device (a sticky error), so it is refused here
   SCFB_REQUIRE(h, ((uintptr_t)d_density | (uintptr_t)d_total_density) % 16 == 0,
                "device density pointers must be 16-byte aligned");
-  if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
-  if (int rc = launch_jk(h, n_spin, d_density, d_total_density)) return rc;
-  if (h->n_ranks > 1 && scfb_peer_ready(h)) {
-    // peer-memory exchange: send to every peer, then wait + sum + accumulate in one kernel
-    if (int rc = scfb_peer_exchange(h, n_spin, d_out)) return rc;
-  } else {
-    const double* jk_final = h->jk;
-    if (h->n_ranks > 1 && h->nccl_comm) {
-      if (int rc = scfb_comm_allreduce_jk(h, n_spin)) return rc;
-      jk_final = h->jk_sum;
-    }
-    if (int rc = scfb_launch_accumulate(h, n_spin, jk_final, d_out)) return rc;
-  }
-  if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
-  return SCFB_OK;
+  return build_jk(h, n_spin, d_density, d_total_density, d_out, nullptr, nullptr);
 }
 
 int scfb_fock_jk(scfb_handle_t h, int n_spin, const double* density, const double* total_density,
@@ -329,18 +389,13 @@ int scfb_fock_jk(scfb_handle_t h, int n_spin, const double* density, const doubl
   if (int rc = check_handle(h)) return rc;
   if (int rc = check_build_args(h, n_spin, density, total_density, out)) return rc;
   if (int rc = stage_inputs(h, n_spin, density, total_density, out)) return rc;
-  if (int rc = scfb_fock_jk_dev(h, n_spin, h->d_density, h->d_total, h->d_out)) return rc;
+  if (int rc = build_jk(h, n_spin, h->d_density, h->d_total, h->d_out, h->ev_side[1], nullptr)) return rc;
   const size_t n2 = (size_t)h->n * h->n;
-  if (is_pinned(out)) {
-    SCFB_CUDA(h, cudaMemcpyAsync(out, h->d_out, n2 * n_spin * sizeof(double), cudaMemcpyDeviceToHost,
-                                 h->stream));
-    SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
-    return scfb_peer_check(h);
-  }
-  SCFB_CUDA(h, cudaMemcpyAsync(h->h_stage + 3 * n2, h->d_out, n2 * n_spin * sizeof(double),
+  const bool pinned = is_pinned(out);
+  SCFB_CUDA(h, cudaMemcpyAsync(pinned ? out : h->h_stage + 3 * n2, h->d_out, n2 * n_spin * sizeof(double),
                                cudaMemcpyDeviceToHost, h->stream));
   SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
-  std::memcpy(out, h->h_stage + 3 * n2, n2 * n_spin * sizeof(double));
+  if (!pinned) std::memcpy(out, h->h_stage + 3 * n2, n2 * n_spin * sizeof(double));
   return scfb_peer_check(h);
 }
 
@@ -350,17 +405,8 @@ int scfb_jk_split(scfb_handle_t h, int n_spin, const double* density, const doub
   if (int rc = check_build_args(h, n_spin, density, total_density, J)) return rc;
   SCFB_REQUIRE(h, K, "null K pointer");
   if (int rc = stage_inputs(h, n_spin, density, total_density, nullptr)) return rc;
-  if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
-  if (int rc = launch_jk(h, n_spin, h->d_density, h->d_total)) return rc;
-  const double* jk_final = h->jk;
-  if (h->n_ranks > 1 && scfb_peer_ready(h)) {
-    if (int rc = scfb_peer_exchange(h, n_spin, nullptr)) return rc;
-    jk_final = h->jk_sum;
-  } else if (h->n_ranks > 1 && h->nccl_comm) {
-    if (int rc = scfb_comm_allreduce_jk(h, n_spin)) return rc;
-    jk_final = h->jk_sum;
-  }
-  if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+  const double* jk_final = nullptr;
+  if (int rc = build_jk(h, n_spin, h->d_density, h->d_total, nullptr, nullptr, &jk_final)) return rc;
   const size_t n2 = (size_t)h->n * h->n;
   SCFB_CUDA(h, cudaMemcpyAsync(h->h_stage, jk_final, (1 + n_spin) * n2 * sizeof(double),
                                cudaMemcpyDeviceToHost, h->stream));

@@ -12,6 +12,16 @@
 
 struct scfb_scf_state;  // dense.cu
 
+// What the full-layout stream kernel's slab finisher does with a finished nu-slab (columns
+// J[:,nu], K_s[:,nu]) beyond storing it in the handle's own jk buffer.  Passed by value to the kernel.
+struct ScfbFuse {
+  double* out = nullptr;  // single rank: out[:,nu,s] += J[:,nu] - K_s[:,nu]  (no separate accumulate launch)
+  int n_peers = 0;        // > 0: store the columns into every rank's landing zone (peer memory over NVLink) ...
+  double* peer_jk[8] = {};                // ... [J | K_a | K_b] of rank r for this build's parity
+  unsigned long long* peer_flag[8] = {};  // this rank's flag word inside rank r's flag array
+  unsigned long long epoch = 0;           // published there by the kernel's last CTA
+};
+
 struct scfb_handle_s {
   int n = 0;             // n_bas
   int layout = SCFB_LAYOUT_FULL;
@@ -29,6 +39,9 @@ struct scfb_handle_s {
   double* eri = nullptr;  // device shard
   uint64_t eri_elems = 0;
   bool eri_ready = false;
+  bool allow_partial = false;   // n_ranks > 1 without an exchange: return this rank's partial instead of failing
+  bool pk_rows_seen_all = false;  // packed layout: the streamed pack (scfb_eri_pack_slabs) covered every owned i
+  uint64_t* slab_seen = nullptr;  // host bitmap of the owned nu-slabs uploaded so far (full layout)
 
   // device scratch
   double* d_density = nullptr;  // n*n*2   (host-pointer API staging)
@@ -39,6 +52,8 @@ struct scfb_handle_s {
   double* kpart = nullptr;      // per-(nu, c-chunk, b-split) partial K rows
   double* jpart = nullptr;      // per-(nu, c-chunk, b-split) partial J values (b_splits > 1)
   int* sched = nullptr;         // work-item counter of the persistent kernels
+  int* slab_done = nullptr;     // per owned nu-slab: finished work items of the running build (K1 fused tail)
+  unsigned int* grid_done = nullptr;  // CTAs of the running K1 launch that have finished
   int n_sm = 0;                 // SM count of this handle's device (lazily queried)
   bool tma_attr[3] = {false, false, false};  // per NSPIN: smem attributes of jk_full_tma_kernel set on this device
   uint32_t* pk_items[2] = {};   // live work items of jk_packed_kernel per spin count (built at first launch)
@@ -49,6 +64,8 @@ struct scfb_handle_s {
 
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  cudaStream_t side = nullptr;  // host-pointer API: `out` travels here, overlapped with the ERI stream
+  cudaEvent_t ev_side[2] = {nullptr, nullptr};  // [d_out free again, d_out uploaded]
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // build start, stream end, build end
   bool timed = false;
   uint64_t launches = 0;
@@ -99,8 +116,8 @@ inline void scfb_split_range(int n, int rank, int n_ranks, int* lo, int* hi) {
 
 // ---- kernels / launchers implemented in the .cu files --------------------------------
 // jk_full.cu
-int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
-                        const double* d_total);            // fills h->jk for owned columns
+int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density, const double* d_total,
+                        const ScfbFuse* fuse, bool* fused);  // fills h->jk for owned columns
 int scfb_launch_accumulate(scfb_handle_s* h, int n_spin, const double* d_jk, double* d_out);  // out += J - K_s
 uint64_t scfb_kpart_elems_full(int n, int n_slabs);
 uint64_t scfb_jpart_elems_full(int n, int n_slabs);
@@ -124,5 +141,14 @@ void scfb_dense_handles_destroy(scfb_handle_s* h);
 // peer.cu
 bool scfb_peer_ready(scfb_handle_s* h);
 void scfb_peer_destroy(scfb_handle_s* h);
-int scfb_peer_exchange(scfb_handle_s* h, int n_spin, double* d_out);  // d_out == nullptr: fill jk_sum
+void scfb_peer_begin(scfb_handle_s* h, ScfbFuse* fuse);
+int scfb_peer_exchange(scfb_handle_s* h, int n_spin, double* d_out, bool pushed);  // d_out == nullptr: fill jk_sum
 int scfb_peer_check(scfb_handle_s* h);
+int scfb_peer_alloc_local(scfb_handle_s* h);
+void scfb_peer_local_ptrs(scfb_handle_s* h, double** area, unsigned long long** flags);
+int scfb_peer_wire(scfb_handle_s* h, double* const* areas, unsigned long long* const* flags);
+inline int scfb_stream_sync_checked(scfb_handle_s* h) {  // every sync that may follow a build reports a peer timeout
+  cudaError_t e_ = cudaStreamSynchronize(h->stream);
+  if (e_ != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "cudaStreamSynchronize -> %s", cudaGetErrorString(e_));
+  return scfb_peer_check(h);
+}

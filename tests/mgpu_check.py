@@ -66,6 +66,37 @@ def main():
     assert np.array_equal(j, 2 * e(3, 250, idx[:, None], idx[None, :]))
     assert np.array_equal(k[:, :, 0], e(idx[:, None], 5, 17, idx[None, :]) + e(idx[:, None], 17, 5, idx[None, :]))
     assert np.array_equal(k[:, :, 1], e(idx[:, None], 255, 255, idx[None, :]))
+    # dense densities at the BASELINE size: the summed result on EVERY rank against the long-double
+    # literal contraction on a nu-slab sample that touches every rank's columns
+    from oracle import c_oracle
+    rng = np.random.default_rng(2560)
+    dens = np.asfortranarray(rng.standard_normal((n, n, 2)))
+    total = np.asfortranarray(rng.standard_normal((n, n)))
+    slabs = sorted({scf_b200.distributed.shard_range(n, r, world)[0] for r in range(world)} | {n - 1})
+    eri_slabs = np.concatenate([c_oracle.hash_eri(n, synth.SEED_ERI, v, v + 1) for v in slabs], axis=3)
+    jr, kr = c_oracle.jk_literal_ld_slabs(np.asfortranarray(eri_slabs), dens, total)
+    for _ in range(2):
+        j, k = b.jk(dens, total)
+        assert np.abs(j[:, slabs] - jr).max() < 1e-12 * np.abs(jr).max()
+        assert np.abs(k[:, slabs, :] - kr).max() < 1e-12 * np.abs(kr).max()
+        out = np.zeros((n, n, 2), order="F")
+        b.add_2e_term(out, dens, total)
+        assert np.abs(out[:, slabs, :] - (jr[:, :, None] - kr)).max() < 1e-12 * np.abs(kr).max()
+    b.close()
+    # packed8 at a size with several i-blocks per rank: dense partials really are summed
+    n = 130
+    b = scf_b200.distributed.sharded_builder(
+        lambda **kw: scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, layout="packed8", **kw), dist,
+        exchange=exchange)
+    da = synth.hash_symmetric_matrix(n, synth.SEED_DA)
+    db = synth.hash_symmetric_matrix(n, synth.SEED_DB)
+    dens = np.asfortranarray(np.stack([da, db], axis=2))
+    slabs = [0, 64, 129]
+    eri_slabs = np.concatenate([c_oracle.hash_eri(n, synth.SEED_ERI, v, v + 1) for v in slabs], axis=3)
+    jr, kr = c_oracle.jk_literal_ld_slabs(np.asfortranarray(eri_slabs), dens, da + db)
+    j, k = b.jk(dens, da + db)
+    assert np.abs(j[:, slabs] - jr).max() < 1e-12 * np.abs(jr).max()
+    assert np.abs(k[:, slabs, :] - kr).max() < 1e-12 * np.abs(kr).max()
     b.close()
     dist.barrier()
     if rank == 0:

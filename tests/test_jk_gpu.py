@@ -173,7 +173,7 @@ def test_shard_partials_sum_to_full(n, n_ranks):
     js, ks = np.zeros_like(jf), np.zeros_like(kf)
     covered = []
     for g in range(n_ranks):
-        part = scf_b200.JKBuilderCUDA.from_tensor(eri, rank=g, n_ranks=n_ranks)
+        part = scf_b200.JKBuilderCUDA.from_tensor(eri, rank=g, n_ranks=n_ranks, allow_partial=True)
         lo, hi = part.shard_range
         assert (lo, hi) == o.shard_range(n, g, n_ranks)
         covered.append((lo, hi))
@@ -224,7 +224,7 @@ def test_error_behaviour():
 def test_wide_rows_known_answers_on_a_shard(n, n_ranks):
     """The full tensor would be 0.6 TB / 66 GB; rank 0 of `n_ranks` owns only a few nu-slabs,
     whose J/K columns have exact closed-form answers for unit densities (hash family)."""
-    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, rank=0, n_ranks=n_ranks)
+    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, rank=0, n_ranks=n_ranks, allow_partial=True)
     lo, hi = b.shard_range
     assert lo == 0 and 0 < hi <= 8
     idx = np.arange(n)
@@ -256,7 +256,7 @@ def test_eighth_shard_with_b_splits_known_answers(n, rank, split, tma, monkeypat
     monkeypatch.setenv("SCFB_FULL_TMA", tma)           # both read when the handle is created / launched
     if split:
         monkeypatch.setenv("SCFB_FULL_BSPLIT", split)
-    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, rank=rank, n_ranks=8)
+    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI, rank=rank, n_ranks=8, allow_partial=True)
     lo, hi = b.shard_range
     assert hi - lo == n // 8
     idx, own = np.arange(n), np.arange(lo, hi)
@@ -300,7 +300,7 @@ def test_device_pointer_api_on_callers_stream(layout):
         for _ in range(3):                                # accumulates: 3 x (J - K)
             b.add_2e_term_device(d_out.data_ptr(), d_dens.data_ptr(), d_total.data_ptr(), n_spin)
     stream.synchronize()
-    assert b.launch_count - before >= 9                   # >= 3 kernels per build
+    assert b.launch_count - before >= 3                   # >= 1 kernel per build (full layout: the fused K1 alone)
     out = d_out.cpu().numpy().T
     assert rel_err(out, 3 * ref) < RTOL
     stream_ms, total_ms = b.last_build_ms()
@@ -318,14 +318,42 @@ def test_chunked_slab_upload_equals_single_upload():
     jw, kw = whole.jk(dens, total)
     whole.close()
     for rank, n_ranks in ((0, 1), (1, 3)):
-        b = scf_b200.JKBuilderCUDA(n, rank=rank, n_ranks=n_ranks)
+        b = scf_b200.JKBuilderCUDA(n, rank=rank, n_ranks=n_ranks, allow_partial=True)
         with pytest.raises(scf_b200.ScfbError):               # not ready yet
             b.jk(dens, total)
-        for first in range(0, n, 4):                          # 4 slabs at a time, ragged tail
+        for first in range(4, n, 4):                          # 4 slabs at a time, ragged tail
             b.upload_slabs(eri[:, :, :, first:first + 4], first)
+        lo, hi = b.shard_range
+        if lo < 4:                                            # slabs 0..3 are still missing: refused
+            with pytest.raises(scf_b200.ScfbError) as exc:
+                b.mark_ready()
+            assert exc.value.code == scf_b200.capi.ERR_STATE
+        b.upload_slabs(eri[:, :, :, 0:4], 0)
         b.mark_ready()
         j, k = b.jk(dens, total)
         lo, hi = b.shard_range
         assert np.array_equal(j[:, lo:hi], jw[:, lo:hi]) and np.array_equal(k[:, lo:hi], kw[:, lo:hi])
         assert np.array_equal(b.eri_shard(), eri[:, :, :, lo:hi])
         b.close()
+
+
+def test_multi_rank_handle_without_exchange_refuses_to_build():
+    """a rank of a multi-rank builder with neither communicator nor peer exchange must not
+    silently return its partial (include/scf_b200.h: SCFB_ERR_STATE unless scfb_allow_partial)."""
+    n = 8
+    rng = np.random.default_rng(5)
+    eri = np.asfortranarray(rng.standard_normal((n, n, n, n)))
+    dens = rng.standard_normal((n, n, 1))
+    b = scf_b200.JKBuilderCUDA.from_tensor(eri, rank=1, n_ranks=2)
+    with pytest.raises(scf_b200.ScfbError) as exc:
+        b.jk(dens, 2 * dens[:, :, 0])
+    assert exc.value.code == scf_b200.capi.ERR_STATE
+    out = np.zeros((n, n, 1), order="F")
+    with pytest.raises(scf_b200.ScfbError):
+        b.add_2e_term(out, dens, 2 * dens[:, :, 0])
+    assert not out.any()
+    b.allow_partial()
+    j, k = b.jk(dens, 2 * dens[:, :, 0])
+    lo, hi = b.shard_range
+    assert j[:, lo:hi].any() and not j[:, :lo].any()
+    b.close()

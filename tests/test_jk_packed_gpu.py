@@ -82,7 +82,7 @@ def test_packed_shard_partials_sum_to_full(n, n_ranks):
     bounds = []
     nbytes = 0
     for g in range(n_ranks):
-        part = scf_b200.JKBuilderCUDA.from_tensor(eri, layout="packed8", rank=g, n_ranks=n_ranks)
+        part = scf_b200.JKBuilderCUDA.from_tensor(eri, layout="packed8", rank=g, n_ranks=n_ranks, allow_partial=True)
         bounds.append(part.shard_range)
         nbytes += part.eri_bytes
         j, k = part.jk(density, total)
