@@ -110,6 +110,10 @@ int scfb_jk_split(scfb_handle_t h, int n_spin, const double* density,
  * handle's stream: `stream_ms` = the ERI-streaming kernel alone, `total_ms` = all
  * launches of the build (stream + reduce + collective + accumulate). */
 int scfb_last_build_ms(scfb_handle_t h, double* stream_ms, double* total_ms);
+/* The same two durations for the last `max_builds` builds (at most 128 are kept), oldest first,
+ * WITHOUT having synchronised between them: what a back-to-back timing loop reads afterwards.
+ * *n_builds = entries written; either array may be NULL. */
+int scfb_build_ms_history(scfb_handle_t h, int max_builds, double* stream_ms, double* total_ms, int* n_builds);
 /* Number of kernels this library launched on this handle since creation. */
 int scfb_launch_count(scfb_handle_t h, uint64_t* launches);
 

@@ -20,6 +20,8 @@ def lib():
         _lib.jk_literal_ld.argtypes = [_dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
         _lib.jk_literal_ld_slabs.argtypes = [_dp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
         _lib.jk_literal_ld_slabs.restype = None
+        _lib.permute_mban_slabs.argtypes = [_dp, C.c_int, C.c_int, _dp]
+        _lib.permute_mban_slabs.restype = None
         _lib.jk_onepass_omp.argtypes = [_dp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, _dp]
         _lib.hash_eri_slabs.argtypes = [_dp, C.c_int, C.c_uint64, C.c_int, C.c_int]
         _lib.chain_eri_slabs.argtypes = [_dp, C.c_int, _dp, C.c_int, C.c_int]
@@ -56,6 +58,16 @@ def jk_literal_ld_slabs(eri_slabs, density, total_density):
     k = np.zeros((n, n_slabs, n_spin), order="F")
     lib().jk_literal_ld_slabs(_p(e), n, n_spin, n_slabs, _p(d), _p(t), _p(j), _p(k))
     return j, k
+
+
+def permute_mban(eri_slabs, out=None):
+    """P[a,b,m,v] = eri_slabs[m,b,a,v] (blocked OpenMP transpose; the K temporary of the reference)."""
+    e = np.asfortranarray(eri_slabs, dtype=np.float64)
+    n, n_slabs = e.shape[0], e.shape[3]
+    if out is None:
+        out = np.empty_like(e, order="F")
+    lib().permute_mban_slabs(_p(e), n, n_slabs, _p(out))
+    return out
 
 
 def jk_onepass(eri_slabs, density, total_density, nu_lo, nu_hi):

@@ -103,6 +103,29 @@ void jk_onepass_omp(const double* eri, int n, int n_spin, const double* density,
   }
 }
 
+/* The permuted temporary the reference's K contraction materialises on a CPU
+ * (JKBuilderFromTensor.jl:37,45-46 `eri[mu,beta,alpha,nu] * D[alpha,beta]`: the open indices (1,4)
+ * cannot be fused, so TensorOperations copies the tensor into contraction order and calls BLAS;
+ * SURVEY.md 8a): P[a,b,m,v] = X[m,b,a,v] for the nu-slabs in `eri_slabs`, as a cache-blocked,
+ * all-core transpose of the (first, third) index pair — what a tuned permute does, so that the
+ * CPU reference arm is not handicapped by a strided NumPy copy. */
+void permute_mban_slabs(const double* eri_slabs, int n, int n_slabs, double* out) {
+  const size_t N = (size_t)n, N2 = N * N, N3 = N2 * N;
+  const int T = 32;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int v = 0; v < n_slabs; ++v)
+    for (int b = 0; b < n; ++b) {
+      const double* X = eri_slabs + (size_t)v * N3 + N * (size_t)b; /* X[m + N2*a] */
+      double* P = out + (size_t)v * N3 + N * (size_t)b;             /* P[a + N2*m] */
+      for (int a0 = 0; a0 < n; a0 += T)
+        for (int m0 = 0; m0 < n; m0 += T) {
+          const int a1 = a0 + T < n ? a0 + T : n, m1 = m0 + T < n ? m0 + T : n;
+          for (int m = m0; m < m1; ++m)
+            for (int a = a0; a < a1; ++a) P[(size_t)a + N2 * (size_t)m] = X[(size_t)m + N2 * (size_t)a];
+        }
+    }
+}
+
 /* ---- synthetic families (DESIGN.md "synthetic inputs"; twins of csrc/eri_gen.cu) ---------- */
 static inline uint64_t pair_index(uint64_t i, uint64_t j) {
   return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i;

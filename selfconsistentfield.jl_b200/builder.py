@@ -161,6 +161,16 @@ class JKBuilderCUDA(TwoElectronBuilder):
         capi.check(capi.lib().scfb_last_build_ms(self._h, C.byref(a), C.byref(b)), self._h)
         return a.value, b.value
 
+    def build_ms_history(self, max_builds=128):
+        """(stream_ms[], total_ms[]) of the last builds (<= 128), oldest first; the builds need not
+        have been synchronised one by one (bench.py reads this after its back-to-back loop)."""
+        a = np.zeros(max_builds)
+        b = np.zeros(max_builds)
+        cnt = C.c_int()
+        capi.check(capi.lib().scfb_build_ms_history(self._h, max_builds, capi.ptr(a), capi.ptr(b), C.byref(cnt)),
+                   self._h)
+        return a[:cnt.value], b[:cnt.value]
+
     @property
     def launch_count(self):
         c = C.c_uint64()

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "scfb_fock_jk_dev": [_h, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
     "scfb_jk_split": [_h, C.c_int, _dp, _dp, _dp, _dp],
     "scfb_last_build_ms": [_h, _dp, _dp],
+    "scfb_build_ms_history": [_h, C.c_int, _dp, _dp, C.POINTER(C.c_int)],
     "scfb_launch_count": [_h, C.POINTER(C.c_uint64)],
     "scfb_scf_setup": [_h, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
     "scfb_scf_n_spin": [_h, C.POINTER(C.c_int)],

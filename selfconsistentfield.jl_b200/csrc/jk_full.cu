@@ -796,15 +796,15 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
   const int n_slabs = h->nu_hi - h->nu_lo;
   if (fused) *fused = false;
   if (n_slabs <= 0) {  // this rank owns nothing: its partial stays zero
-    if (h->timed) cudaEventRecord(h->ev[3], h->stream);
-    if (h->timed) cudaEventRecord(h->ev[1], h->stream);
+    if (h->timed) cudaEventRecord(scfb_ev(h, 3), h->stream);
+    if (h->timed) cudaEventRecord(scfb_ev(h, 1), h->stream);
     return SCFB_OK;
   }
   const bool even = (n % 2 == 0);
   // VEC=2 needs R = n/2 <= MAX_THREADS; wider rows fall back to more rows per thread? no:
   // rows longer than 2*MAX_THREADS are rejected at create time.
   cudaError_t e;
-  if (h->timed) cudaEventRecord(h->ev[3], h->stream);
+  if (h->timed) cudaEventRecord(scfb_ev(h, 3), h->stream);
   const bool wide = (even ? n / 2 : n) > MAX_THREADS;  // rows longer than one 256-thread pass
   const bool tma = tma_path(n);  // SCFB_FULL_TMA=0 selects the register-prefetch (LDG) kernel
   const bool in_kernel_tail = tma && h->b_splits == 1;
@@ -830,7 +830,7 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
                     : launch_stream<1, 2, 512>(h, d_density, d_total);
   if (e != cudaSuccess)
     return scfb_fail(h, SCFB_ERR_CUDA, "jk_full_stream_kernel launch: %s", cudaGetErrorString(e));
-  if (h->timed) cudaEventRecord(h->ev[1], h->stream);
+  if (h->timed) cudaEventRecord(scfb_ev(h, 1), h->stream);
   if (in_kernel_tail) {  // K rows were reduced by the slab finishers
     h->launches += 1;
     return SCFB_OK;

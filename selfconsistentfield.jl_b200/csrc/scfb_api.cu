@@ -89,7 +89,8 @@ int build_jk(scfb_handle_s* h, int n_spin, const double* d_density, const double
   else if (!use_nccl && !out_event)
     fuse.out = d_out;  // single rank: the slab finishers accumulate, no further launch
   bool fused = false;
-  if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+  ++h->build_no;
+  if (h->timed) SCFB_CUDA(h, cudaEventRecord(scfb_ev(h, 0), h->stream));
   if (int rc = h->layout == SCFB_LAYOUT_FULL ? scfb_launch_jk_full(h, n_spin, d_density, d_total, &fuse, &fused)
                                              : scfb_launch_jk_packed(h, n_spin, d_density, d_total))
     return rc;
@@ -106,7 +107,7 @@ int build_jk(scfb_handle_s* h, int n_spin, const double* d_density, const double
     if (d_out && !(fused && fuse.out))
       if (int rc = scfb_launch_accumulate(h, n_spin, jk, d_out)) return rc;
   }
-  if (h->timed) SCFB_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+  if (h->timed) SCFB_CUDA(h, cudaEventRecord(scfb_ev(h, 2), h->stream));
   if (jk_final) *jk_final = jk;
   return SCFB_OK;
 }
@@ -172,7 +173,8 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
 
   CREATE_CUDA(cudaSetDevice(device));
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  for (auto& ev : h->ev) CREATE_CUDA(cudaEventCreate(&ev));
+  for (auto& slot : h->ev_ring)
+    for (auto& ev : slot) CREATE_CUDA(cudaEventCreate(&ev));
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   for (auto& ev : h->ev_side) CREATE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   h->timed = true;
@@ -234,8 +236,9 @@ int scfb_destroy(scfb_handle_t h) {
   for (auto* p : h->pk_items) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   std::free(h->slab_seen);
-  for (auto& ev : h->ev)
-    if (ev) cudaEventDestroy(ev);
+  for (auto& slot : h->ev_ring)
+    for (auto& ev : slot)
+      if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->ev_side)
     if (ev) cudaEventDestroy(ev);
   if (h->side) cudaStreamDestroy(h->side);
@@ -418,12 +421,33 @@ int scfb_jk_split(scfb_handle_t h, int n_spin, const double* density, const doub
 
 int scfb_last_build_ms(scfb_handle_t h, double* stream_ms, double* total_ms) {
   if (int rc = check_handle(h)) return rc;
-  SCFB_CUDA(h, cudaEventSynchronize(h->ev[2]));
+  if (h->build_no == 0) return scfb_fail(h, SCFB_ERR_STATE, "no build has run on this handle");
+  SCFB_CUDA(h, cudaEventSynchronize(scfb_ev(h, 2)));
   float a = 0.f, b = 0.f;
-  SCFB_CUDA(h, cudaEventElapsedTime(&a, h->ev[3], h->ev[1]));
-  SCFB_CUDA(h, cudaEventElapsedTime(&b, h->ev[0], h->ev[2]));
+  SCFB_CUDA(h, cudaEventElapsedTime(&a, scfb_ev(h, 3), scfb_ev(h, 1)));
+  SCFB_CUDA(h, cudaEventElapsedTime(&b, scfb_ev(h, 0), scfb_ev(h, 2)));
   if (stream_ms) *stream_ms = a;
   if (total_ms) *total_ms = b;
+  return SCFB_OK;
+}
+
+int scfb_build_ms_history(scfb_handle_t h, int max_builds, double* stream_ms, double* total_ms, int* n_builds) {
+  if (int rc = check_handle(h)) return rc;
+  SCFB_REQUIRE(h, max_builds >= 0 && n_builds, "bad arguments");
+  int count = max_builds;
+  if ((uint64_t)count > h->build_no) count = (int)h->build_no;
+  if (count > SCFB_EV_RING) count = SCFB_EV_RING;
+  *n_builds = count;
+  if (count == 0) return SCFB_OK;
+  SCFB_CUDA(h, cudaEventSynchronize(scfb_ev(h, 2)));
+  for (int i = 0; i < count; ++i) {  // oldest first
+    cudaEvent_t* ev = h->ev_ring[(h->build_no - count + i) % SCFB_EV_RING];
+    float a = 0.f, b = 0.f;
+    SCFB_CUDA(h, cudaEventElapsedTime(&a, ev[3], ev[1]));
+    SCFB_CUDA(h, cudaEventElapsedTime(&b, ev[0], ev[2]));
+    if (stream_ms) stream_ms[i] = a;
+    if (total_ms) total_ms[i] = b;
+  }
   return SCFB_OK;
 }
 

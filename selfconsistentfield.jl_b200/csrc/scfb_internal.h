@@ -12,6 +12,8 @@
 
 struct scfb_scf_state;  // dense.cu
 
+constexpr int SCFB_EV_RING = 128;
+
 // What the full-layout stream kernel's slab finisher does with a finished nu-slab (columns
 // J[:,nu], K_s[:,nu]) beyond storing it in the handle's own jk buffer.  Passed by value to the kernel.
 struct ScfbFuse {
@@ -66,7 +68,9 @@ struct scfb_handle_s {
   bool own_stream = true;
   cudaStream_t side = nullptr;  // host-pointer API: `out` travels here, overlapped with the ERI stream
   cudaEvent_t ev_side[2] = {nullptr, nullptr};  // [d_out free again, d_out uploaded]
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // build start, stream end, build end
+  // CUDA-event timing of the last SCFB_EV_RING builds: [build start, stream-kernel end, build end, stream-kernel start]
+  cudaEvent_t ev_ring[SCFB_EV_RING][4] = {};
+  uint64_t build_no = 0;  // builds started on this handle; build b uses ring slot b % SCFB_EV_RING
   bool timed = false;
   uint64_t launches = 0;
 
@@ -79,6 +83,9 @@ struct scfb_handle_s {
 
   char err[512] = {0};
 };
+
+// event i of the build in progress (or, between builds, of the last one)
+inline cudaEvent_t scfb_ev(scfb_handle_s* h, int i) { return h->ev_ring[(h->build_no + SCFB_EV_RING - 1) % SCFB_EV_RING][i]; }
 
 // thread-local message for calls that fail before a handle exists
 extern thread_local char scfb_tls_err[512];

@@ -17,7 +17,7 @@ from oracle import synth  # noqa: E402
 
 def test_reference_arm_json_line():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
-                        "--n-bas", "32", "--cpu-slabs", "4", "--steps", "2", "--warmup", "1"],
+                        "--n-bas", "32", "--cpu-slabs", "4", "--steps", "4", "--warmup", "2"],
                        capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stderr
     lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
@@ -25,9 +25,13 @@ def test_reference_arm_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "fock_builds_per_s" and d["unit"] == "Fock builds/s"
     assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["data"] == "synthetic"
-    assert d["vs_baseline"] is None and d["value"] > 0 and "workload" in d["config"]
+    assert d["vs_baseline"] is None and d["value"] > 0
+    assert d["steps"] == 4 and d["warmup"] == 2                 # the driver's counts are honoured
+    # same config keys (and values) as our arm emits for the same arguments
+    assert d["config"] == bench.config_dict(32, 2, "full", 1, "p2p")
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert "4 of 32 nu-slabs" in cb["sample"] and "scaled x32/4" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
 
@@ -40,19 +44,18 @@ def test_reference_arm_other_ranks_print_nothing():
 
 
 def test_timed_cpu_strategy_is_the_reference_contraction():
+    """What the CPU arm times (GEMV for J, blocked permute + GEMV per K line) is the reference's
+    contraction: its result equals the oracle's add_2e_term on the sampled nu-slabs."""
     n, s = 12, 5
-    eri = synth.hash_eri(n, nu_lo=2, nu_hi=2 + s)
-    da, db = synth.hash_symmetric_matrix(n, 2), synth.hash_symmetric_matrix(n, 3)
-    out = bench.reference_strategy_slabs(eri, [da, db], da + db)
+    ref_arm = bench.CpuReference(n, 2, s)
+    out = ref_arm.one_pass()
     full = synth.hash_eri(n)
+    da, db = synth.hash_symmetric_matrix(n, synth.SEED_DA), synth.hash_symmetric_matrix(n, synth.SEED_DB)
     ref = o.add_2e_term(np.zeros((n, n, 2)), full, np.stack([da, db], axis=2), da + db)
     for sp in range(2):
-        assert np.abs(out[sp] - ref[:, 2:2 + s, sp]).max() < 1e-12 * np.abs(ref).max()
+        assert np.abs(out[sp] - ref[:, :s, sp]).max() < 1e-12 * np.abs(ref).max()
 
 
 def test_workload_bytes():
-    class A:
-        layout, n_bas, n_spin = "full", 256, 2
-    assert bench.eri_total_bytes(A) == 8 * 256 ** 4
-    A.layout, A.n_bas = "packed8", 384
-    assert bench.eri_total_bytes(A) == 21856961280
+    assert bench.eri_total_bytes(256, "full") == 8 * 256 ** 4
+    assert bench.eri_total_bytes(384, "packed8") == 21856961280
