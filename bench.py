@@ -177,18 +177,37 @@ class CpuReference:
     NumPy/OpenBLAS on every host core.  One pass over S of n slabs costs S/n of a build (the work is
     linear in the slab count), so builds/s = 1 / (t_pass * n / S)."""
 
-    def __init__(self, n, n_spin, n_slabs=0):
+    def __init__(self, n, n_spin, n_slabs=0, passes=4, budget_s=100.0):
+        """n_slabs = 0: the sample is sized so that `passes` passes take about `budget_s` seconds
+        (calibrated on a ~1 GB pass), capped by the tensor itself ("full tensor") and by host RAM."""
         from oracle import c_oracle, synth
         self.c_oracle = c_oracle
         self.n, self.n_spin = n, n_spin
-        if n_slabs <= 0:
-            n_slabs = max(1, int(round(1.07e9 / (8.0 * n ** 3))))       # ~1 GB of tensor per pass
-        self.n_slabs = min(n_slabs, n)
-        self.eri = c_oracle.hash_eri(n, synth.SEED_ERI, 0, self.n_slabs)  # (n,n,n,S) F-ordered
         da = synth.hash_symmetric_matrix(n, synth.SEED_DA)
         db = synth.hash_symmetric_matrix(n, synth.SEED_DB)
         self.dens = [da, db][:n_spin]
         self.total = 2 * da if n_spin == 1 else da + db
+        auto = n_slabs <= 0
+        self._alloc(min(n, n_slabs if not auto else max(1, int(round(1.07e9 / (8.0 * n ** 3))))))
+        if auto and self.n_slabs < n:
+            self.one_pass()
+            t0 = time.perf_counter()
+            self.one_pass()
+            t1 = time.perf_counter() - t0
+            want = int(self.n_slabs * (budget_s / max(passes, 1)) / max(t1, 1e-6))
+            try:
+                avail = int(next(ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")).split()[1]) * 1024
+            except (OSError, StopIteration):
+                avail = 8 << 30
+            want = min(want, int(0.5 * avail / (2 * 8.0 * n ** 3)), n)
+            if want > self.n_slabs:
+                self._alloc(want)
+
+    def _alloc(self, n_slabs):
+        from oracle import synth
+        self.n_slabs = n_slabs
+        self.eri = self.tmp = None
+        self.eri = self.c_oracle.hash_eri(self.n, synth.SEED_ERI, 0, n_slabs)   # (n,n,n,S) F-ordered
         self.tmp = np.empty_like(self.eri, order="F")
 
     def one_pass(self):
@@ -204,14 +223,15 @@ class CpuReference:
 
     def describe(self, t_pass, passes):
         n, s = self.n, self.n_slabs
-        return (f"{s} of {n} nu-slabs of the same n_bf={n} hash tensor ({8 * n ** 3 * s / 1e9:.2f} GB per pass), "
+        return (f"{'the full tensor: ' if s == n else ''}{s} of {n} nu-slabs of the same n_bf={n} hash tensor "
+                f"({8 * n ** 3 * s / 1e9:.2f} GB per pass), "
                 f"OpenBLAS GEMV for J + blocked OpenMP permute + GEMV per spin for K, median of {passes} passes "
                 f"({t_pass:.3f} s each), scaled x{n}/{s} to one full build (work is linear in the slab count)")
 
 
 def cpu_baseline_leg(n, n_spin, n_slabs, passes):
     """The cpu_baseline object of our arm's line (rank 0, N = 1)."""
-    ref = CpuReference(n, n_spin, n_slabs)
+    ref = CpuReference(n, n_spin, n_slabs, passes + 1, 20.0)
     times = []
     for _ in range(passes + 1):
         t0 = time.perf_counter()
@@ -238,7 +258,7 @@ def run_reference(a, rank, world):
     over the bounded slab sample; value = K steps / their time, scaled to full builds."""
     if rank != 0:
         return
-    ref = CpuReference(a.n_bas, a.n_spin, a.cpu_slabs)
+    ref = CpuReference(a.n_bas, a.n_spin, a.cpu_slabs, a.steps + a.warmup, 100.0)
     for _ in range(a.warmup):
         ref.one_pass()
     t0 = time.perf_counter()

@@ -9,9 +9,12 @@
  *     `scfb_last_error(h)` gives the message.  Nothing throws or aborts across the ABI.
  *   - Host entry points are synchronous: outputs are valid on return.
  *   - A handle is driven by ONE caller thread at a time (not re-entrant).
- *   - One handle owns the ERI shard of ONE GPU.  Multi-GPU = one process (or thread)
- *     per GPU, each with its own handle created with (rank, n_ranks); rank g owns the
- *     contiguous nu-slabs (slowest ERI index) `scfb_shard_range` reports.
+ *   - Multi-GPU, two ways.  (a) scfb_create_multi: ONE handle that owns the shards of G devices
+ *     of this process — what a single-threaded caller such as the reference's run_scf needs; every
+ *     entry point below works on it unchanged.  (b) One process (or thread) per GPU, each with its
+ *     own handle created with (rank, n_ranks) plus an exchange (scfb_comm_init or scfb_peer_*).
+ *     Either way rank / member g owns the contiguous nu-slabs (slowest ERI index; packed8: first
+ *     indices i) `scfb_shard_range` reports.
  *
  * Reference interfaces replaced (paths relative to the reference repository):
  *   src/types/ScfProblem.jl:2-9                 abstract TwoElectronBuilder + add_2e_term!
@@ -59,6 +62,13 @@ int scfb_version(void);
 /* Creates a builder for an n_bas^4 ERI on CUDA device `device`.  (rank, n_ranks) select
  * the nu-slab shard this handle owns; use (0, 1) for a single GPU.  Allocates the shard. */
 int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank, int n_ranks);
+/* One handle over n_dev devices of THIS process (device ordinals dev_ids[0..n_dev), <= 8, all
+ * peer-accessible: one NVSwitch box).  Member g owns shard g of n_dev; a build fans the densities
+ * out to every device, every device streams its shard, finished J/K columns travel over peer
+ * memory (NVLink) and the result lands on dev_ids[0] — where the host-pointer calls read it back
+ * and where the device-pointer / scfb_scf_* calls expect their device arrays.  The caller stays
+ * single-threaded (src/run_scf.jl:4-65 unchanged).  n_dev == 1 is scfb_create(.., dev_ids[0], 0, 1). */
+int scfb_create_multi(scfb_handle_t* out, int n_bas, int layout, int n_dev, const int* dev_ids);
 int scfb_destroy(scfb_handle_t h); /* idempotent on NULL */
 const char* scfb_last_error(scfb_handle_t h); /* h may be NULL: last error of this thread */
 int scfb_sync(scfb_handle_t h);

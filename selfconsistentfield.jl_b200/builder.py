@@ -33,16 +33,26 @@ class JKBuilderCUDA(TwoElectronBuilder):
     n_bas       number of basis functions
     layout      "full" (n^4 fp64, Julia order) or "packed8"
     device      CUDA device ordinal
+    devices     list of device ordinals: one builder sharded over several GPUs of this process
     rank,n_ranks  nu-slab shard owned by this builder (one builder per GPU/process)
     """
 
-    def __init__(self, n_bas, layout="full", device=0, rank=0, n_ranks=1, allow_partial=False):
+    def __init__(self, n_bas, layout="full", device=0, rank=0, n_ranks=1, allow_partial=False, devices=None):
         self._h = capi._h()
         self.n_bas = int(n_bas)
         self.layout = layout
         self.device = device
         self.rank, self.n_ranks = rank, n_ranks
         lay = {"full": capi.LAYOUT_FULL, "packed8": capi.LAYOUT_PACKED8}[layout]
+        if devices is not None:
+            # ONE builder over several GPUs of this process (scfb_create_multi): the single-threaded
+            # caller of the reference's run_scf keeps calling add_2e_term once per Fock build
+            assert rank == 0 and n_ranks == 1, "devices= and (rank, n_ranks) are mutually exclusive"
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self.device, self.devices = int(devices[0]), tuple(int(d) for d in devices)
+            capi.check(capi.lib().scfb_create_multi(C.byref(self._h), self.n_bas, lay, len(devices), devs))
+            return
+        self.devices = (device,)
         capi.check(capi.lib().scfb_create(C.byref(self._h), self.n_bas, lay, device, rank, n_ranks))
         if allow_partial:
             self.allow_partial()

@@ -35,6 +35,7 @@ _h = C.c_void_p
 _SIGNATURES = {
     "scfb_version": [],
     "scfb_create": [C.POINTER(_h), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
+    "scfb_create_multi": [C.POINTER(_h), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)],
     "scfb_destroy": [_h],
     "scfb_last_error": [_h],
     "scfb_sync": [_h],

@@ -20,7 +20,18 @@ int check_handle(scfb_handle_s* h) {
   return SCFB_OK;
 }
 
-bool is_pinned(const void* p) {
+// Members of the handle's group (a plain handle is its own only member); other members' errors
+// are copied into the caller-visible handle.
+int n_members(scfb_handle_s* h) { return h->multi ? scfb_multi_n_dev(h) : 1; }
+scfb_handle_s* member(scfb_handle_s* h, int g) { return h->multi ? scfb_multi_member(h, g) : h; }
+int lift(scfb_handle_s* h, scfb_handle_s* m, int rc) {
+  if (rc != SCFB_OK && m != h) std::snprintf(h->err, sizeof h->err, "device %d: %.480s", m->device, m->err);
+  return rc;
+}
+
+}  // namespace
+
+bool scfb_is_pinned(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();  // unregistered host memory on old drivers: clear the sticky error
@@ -34,10 +45,10 @@ bool is_pinned(const void* p) {
 // the handle's pinned staging buffer (one memcpy + one H2D copy).  density / total_density travel on
 // the build stream (the stream kernel needs them); `out` — only needed by the final accumulate —
 // travels on the handle's side stream so that its PCIe time hides behind the ERI stream.
-int stage_inputs(scfb_handle_s* h, int n_spin, const double* density, const double* total,
-                 const double* out) {
+int scfb_stage_inputs(scfb_handle_s* h, int n_spin, const double* density, const double* total,
+                      const double* out) {
   const size_t n2 = (size_t)h->n * h->n;
-  const bool pinned = is_pinned(density) && is_pinned(total) && (!out || is_pinned(out));
+  const bool pinned = scfb_is_pinned(density) && scfb_is_pinned(total) && (!out || scfb_is_pinned(out));
   const double* src_d = density;
   const double* src_t = total;
   const double* src_o = out;
@@ -62,10 +73,12 @@ int stage_inputs(scfb_handle_s* h, int n_spin, const double* density, const doub
   return SCFB_OK;
 }
 
-int check_build_args(scfb_handle_s* h, int n_spin, const void* a, const void* b, const void* c) {
+int scfb_check_build_args(scfb_handle_s* h, int n_spin, const void* a, const void* b, const void* c) {
   SCFB_REQUIRE(h, n_spin == 1 || n_spin == 2, "n_spin must be 1 or 2 (got %d)", n_spin);
   SCFB_REQUIRE(h, a && b && c, "null array pointer");
-  if (!h->eri_ready) return scfb_fail(h, SCFB_ERR_STATE, "ERI not loaded: call scfb_eri_upload/_generate first");
+  for (int g = 0; g < n_members(h); ++g)
+    if (!member(h, g)->eri_ready)
+      return scfb_fail(h, SCFB_ERR_STATE, "ERI not loaded: call scfb_eri_upload/_generate first");
   if (h->n_ranks > 1 && !h->nccl_comm && !scfb_peer_ready(h) && !h->allow_partial)
     return scfb_fail(h, SCFB_ERR_STATE,
                      "rank %d of %d has no cross-GPU exchange (scfb_comm_init / scfb_peer_import): the result "
@@ -79,8 +92,8 @@ int check_build_args(scfb_handle_s* h, int n_spin, const void* a, const void* b,
 // [J | K_a | K_b] lives afterwards.  `out_event`: d_out becomes valid only once this event (recorded on
 // another stream) has fired — waited for right before the first kernel that touches d_out, and it
 // rules out accumulating inside the stream kernel.
-int build_jk(scfb_handle_s* h, int n_spin, const double* d_density, const double* d_total, double* d_out,
-             cudaEvent_t out_event, const double** jk_final) {
+int scfb_build_jk(scfb_handle_s* h, int n_spin, const double* d_density, const double* d_total, double* d_out,
+                  cudaEvent_t out_event, const double** jk_final) {
   const bool use_peer = h->n_ranks > 1 && scfb_peer_ready(h);
   const bool use_nccl = h->n_ranks > 1 && !use_peer && h->nccl_comm;
   ScfbFuse fuse{};
@@ -111,8 +124,6 @@ int build_jk(scfb_handle_s* h, int n_spin, const double* d_density, const double
   if (jk_final) *jk_final = jk;
   return SCFB_OK;
 }
-
-}  // namespace
 
 extern "C" {
 
@@ -215,6 +226,7 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
 
 int scfb_destroy(scfb_handle_t h) {
   if (!h) return SCFB_OK;
+  if (h->multi) scfb_multi_destroy(h);  // the other members of a multi-GPU group go first
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   scfb_comm_destroy(h);
@@ -249,6 +261,11 @@ int scfb_destroy(scfb_handle_t h) {
 
 int scfb_sync(scfb_handle_t h) {
   if (int rc = check_handle(h)) return rc;
+  if (h->multi) {
+    const int rc = scfb_multi_sync(h);
+    cudaSetDevice(h->device);
+    return rc;
+  }
   SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
   return scfb_peer_check(h);
 }
@@ -265,18 +282,21 @@ int scfb_set_stream(scfb_handle_t h, void* cuda_stream) {
 int scfb_shard_range(scfb_handle_t h, int* nu_lo, int* nu_hi) {
   if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
   const bool full = h->layout == SCFB_LAYOUT_FULL;
-  if (nu_lo) *nu_lo = full ? h->nu_lo : h->i_lo;
-  if (nu_hi) *nu_hi = full ? h->nu_hi : h->i_hi;
+  if (nu_lo) *nu_lo = h->multi ? 0 : (full ? h->nu_lo : h->i_lo);  // a multi-GPU group owns everything
+  if (nu_hi) *nu_hi = h->multi ? h->n : (full ? h->nu_hi : h->i_hi);
   return SCFB_OK;
 }
 
 int scfb_eri_bytes(scfb_handle_t h, uint64_t* bytes) {
   if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
-  if (bytes) *bytes = h->eri_elems * sizeof(double);
+  if (bytes) {
+    *bytes = 0;
+    for (int g = 0; g < n_members(h); ++g) *bytes += member(h, g)->eri_elems * sizeof(double);
+  }
   return SCFB_OK;
 }
 
-int scfb_eri_upload_slabs(scfb_handle_t h, const double* host_slabs, int nu_first, int nu_count) {
+static int one_eri_upload_slabs(scfb_handle_t h, const double* host_slabs, int nu_first, int nu_count) {
   if (int rc = check_handle(h)) return rc;
   SCFB_REQUIRE(h, host_slabs, "null host pointer");
   SCFB_REQUIRE(h, h->layout == SCFB_LAYOUT_FULL, "slab upload is for the full layout; use scfb_eri_upload");
@@ -301,7 +321,7 @@ int scfb_eri_upload_slabs(scfb_handle_t h, const double* host_slabs, int nu_firs
   return SCFB_OK;
 }
 
-int scfb_eri_upload(scfb_handle_t h, const double* host_eri) {
+static int one_eri_upload(scfb_handle_t h, const double* host_eri) {
   if (h && h->layout == SCFB_LAYOUT_PACKED8) {
     if (int rc = check_handle(h)) return rc;
     SCFB_REQUIRE(h, host_eri, "null host pointer");
@@ -318,12 +338,12 @@ int scfb_eri_upload(scfb_handle_t h, const double* host_eri) {
     h->eri_ready = true;
     return SCFB_OK;
   }
-  int rc = scfb_eri_upload_slabs(h, host_eri, 0, h ? h->n : 0);
+  int rc = one_eri_upload_slabs(h, host_eri, 0, h ? h->n : 0);
   if (rc == SCFB_OK) h->eri_ready = true;
   return rc;
 }
 
-int scfb_eri_mark_ready(scfb_handle_t h) {  // after a sequence of partial slab uploads
+static int one_eri_mark_ready(scfb_handle_t h) {  // after a sequence of partial slab uploads
   if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
   if (h->eri_ready) return SCFB_OK;
   if (h->layout == SCFB_LAYOUT_FULL)
@@ -343,7 +363,7 @@ int scfb_allow_partial(scfb_handle_t h, int allow) {
   return SCFB_OK;
 }
 
-int scfb_eri_generate(scfb_handle_t h, int family, uint64_t seed, const double* aux) {
+static int one_eri_generate(scfb_handle_t h, int family, uint64_t seed, const double* aux) {
   if (int rc = check_handle(h)) return rc;
   SCFB_REQUIRE(h, family == SCFB_ERI_HASH || family == SCFB_ERI_CHAIN, "unknown family %d", family);
   double* d_aux = nullptr;
@@ -367,7 +387,7 @@ int scfb_eri_generate(scfb_handle_t h, int family, uint64_t seed, const double* 
   return SCFB_OK;
 }
 
-int scfb_eri_download(scfb_handle_t h, double* host_shard) {
+static int one_eri_download(scfb_handle_t h, double* host_shard) {
   if (int rc = check_handle(h)) return rc;
   SCFB_REQUIRE(h, host_shard, "null host pointer");  // packed: raw pre-scaled packed rows
   SCFB_CUDA(h, cudaMemcpyAsync(host_shard, h->eri, h->eri_elems * sizeof(double),
@@ -376,28 +396,72 @@ int scfb_eri_download(scfb_handle_t h, double* host_shard) {
   return SCFB_OK;
 }
 
+// ---- the same entry points over every member of a multi-GPU group ----
+#define SCFB_EACH_MEMBER(h, call)                              \
+  do {                                                         \
+    if (!(h)) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle"); \
+    for (int g_ = 0; g_ < n_members(h); ++g_) {                \
+      scfb_handle_s* m = member(h, g_);                        \
+      if (int rc_ = lift(h, m, call)) {                        \
+        cudaSetDevice((h)->device);                            \
+        return rc_;                                            \
+      }                                                        \
+    }                                                          \
+    cudaSetDevice((h)->device);                                \
+    return SCFB_OK;                                            \
+  } while (0)
+
+int scfb_eri_upload_slabs(scfb_handle_t h, const double* host_slabs, int nu_first, int nu_count) {
+  SCFB_EACH_MEMBER(h, one_eri_upload_slabs(m, host_slabs, nu_first, nu_count));
+}
+int scfb_eri_upload(scfb_handle_t h, const double* host_eri) { SCFB_EACH_MEMBER(h, one_eri_upload(m, host_eri)); }
+int scfb_eri_mark_ready(scfb_handle_t h) { SCFB_EACH_MEMBER(h, one_eri_mark_ready(m)); }
+int scfb_eri_generate(scfb_handle_t h, int family, uint64_t seed, const double* aux) {
+  SCFB_EACH_MEMBER(h, one_eri_generate(m, family, seed, aux));
+}
+int scfb_eri_download(scfb_handle_t h, double* host_shard) {  // members' shards back to back (rank order)
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  SCFB_REQUIRE(h, host_shard, "null host pointer");
+  for (int g = 0; g < n_members(h); ++g) {
+    scfb_handle_s* m = member(h, g);
+    if (int rc = lift(h, m, one_eri_download(m, host_shard))) return rc;
+    host_shard += m->eri_elems;
+  }
+  cudaSetDevice(h->device);
+  return SCFB_OK;
+}
+
 int scfb_fock_jk_dev(scfb_handle_t h, int n_spin, const double* d_density,
                      const double* d_total_density, double* d_out) {
   if (int rc = check_handle(h)) return rc;
-  if (int rc = check_build_args(h, n_spin, d_density, d_total_density, d_out)) return rc;
+  if (int rc = scfb_check_build_args(h, n_spin, d_density, d_total_density, d_out)) return rc;
   // the kernels read the densities with 128-bit loads / 16-byte-granular bulk copies: a misaligned
   // pointer would fault on the device (a sticky error), so it is refused here
   SCFB_REQUIRE(h, ((uintptr_t)d_density | (uintptr_t)d_total_density) % 16 == 0,
                "device density pointers must be 16-byte aligned");
-  return build_jk(h, n_spin, d_density, d_total_density, d_out, nullptr, nullptr);
+  if (h->multi) return scfb_multi_build_dev(h, n_spin, d_density, d_total_density, d_out, nullptr, nullptr, true);
+  return scfb_build_jk(h, n_spin, d_density, d_total_density, d_out, nullptr, nullptr);
 }
 
 int scfb_fock_jk(scfb_handle_t h, int n_spin, const double* density, const double* total_density,
                  double* out) {
   if (int rc = check_handle(h)) return rc;
-  if (int rc = check_build_args(h, n_spin, density, total_density, out)) return rc;
-  if (int rc = stage_inputs(h, n_spin, density, total_density, out)) return rc;
-  if (int rc = build_jk(h, n_spin, h->d_density, h->d_total, h->d_out, h->ev_side[1], nullptr)) return rc;
+  if (int rc = scfb_check_build_args(h, n_spin, density, total_density, out)) return rc;
+  if (h->multi) {
+    if (int rc = scfb_multi_stage_inputs(h, n_spin, density, total_density, out)) return rc;
+    if (int rc = scfb_multi_build_dev(h, n_spin, h->d_density, h->d_total, h->d_out, h->ev_side[1], nullptr, false))
+      return rc;
+  } else {
+    if (int rc = scfb_stage_inputs(h, n_spin, density, total_density, out)) return rc;
+    if (int rc = scfb_build_jk(h, n_spin, h->d_density, h->d_total, h->d_out, h->ev_side[1], nullptr)) return rc;
+  }
   const size_t n2 = (size_t)h->n * h->n;
-  const bool pinned = is_pinned(out);
+  const bool pinned = scfb_is_pinned(out);
   SCFB_CUDA(h, cudaMemcpyAsync(pinned ? out : h->h_stage + 3 * n2, h->d_out, n2 * n_spin * sizeof(double),
                                cudaMemcpyDeviceToHost, h->stream));
   SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->multi)
+    if (int rc = scfb_multi_inputs_consumed(h)) return rc;
   if (!pinned) std::memcpy(out, h->h_stage + 3 * n2, n2 * n_spin * sizeof(double));
   return scfb_peer_check(h);
 }
@@ -405,15 +469,22 @@ int scfb_fock_jk(scfb_handle_t h, int n_spin, const double* density, const doubl
 int scfb_jk_split(scfb_handle_t h, int n_spin, const double* density, const double* total_density,
                   double* J, double* K) {
   if (int rc = check_handle(h)) return rc;
-  if (int rc = check_build_args(h, n_spin, density, total_density, J)) return rc;
+  if (int rc = scfb_check_build_args(h, n_spin, density, total_density, J)) return rc;
   SCFB_REQUIRE(h, K, "null K pointer");
-  if (int rc = stage_inputs(h, n_spin, density, total_density, nullptr)) return rc;
   const double* jk_final = nullptr;
-  if (int rc = build_jk(h, n_spin, h->d_density, h->d_total, nullptr, nullptr, &jk_final)) return rc;
+  if (h->multi) {
+    if (int rc = scfb_multi_stage_inputs(h, n_spin, density, total_density, nullptr)) return rc;
+    if (int rc = scfb_multi_build_dev(h, n_spin, h->d_density, h->d_total, nullptr, nullptr, &jk_final, false)) return rc;
+  } else {
+    if (int rc = scfb_stage_inputs(h, n_spin, density, total_density, nullptr)) return rc;
+    if (int rc = scfb_build_jk(h, n_spin, h->d_density, h->d_total, nullptr, nullptr, &jk_final)) return rc;
+  }
   const size_t n2 = (size_t)h->n * h->n;
   SCFB_CUDA(h, cudaMemcpyAsync(h->h_stage, jk_final, (1 + n_spin) * n2 * sizeof(double),
                                cudaMemcpyDeviceToHost, h->stream));
   SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->multi)
+    if (int rc = scfb_multi_inputs_consumed(h)) return rc;
   std::memcpy(J, h->h_stage, n2 * sizeof(double));
   std::memcpy(K, h->h_stage + n2, n2 * n_spin * sizeof(double));
   return scfb_peer_check(h);
@@ -453,7 +524,10 @@ int scfb_build_ms_history(scfb_handle_t h, int max_builds, double* stream_ms, do
 
 int scfb_launch_count(scfb_handle_t h, uint64_t* launches) {
   if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
-  if (launches) *launches = h->launches;
+  if (launches) {
+    *launches = 0;
+    for (int g = 0; g < n_members(h); ++g) *launches += member(h, g)->launches;
+  }
   return SCFB_OK;
 }
 

@@ -11,6 +11,7 @@
 #include "../../include/scf_b200.h"
 
 struct scfb_scf_state;  // dense.cu
+struct scfb_multi_s;     // multi.cu
 
 constexpr int SCFB_EV_RING = 128;
 
@@ -75,6 +76,7 @@ struct scfb_handle_s {
   uint64_t launches = 0;
 
   scfb_scf_state* scf = nullptr;  // device-resident SCF step (scfb_scf_setup)
+  scfb_multi_s* multi = nullptr;  // set on member 0 of a single-process multi-GPU group (scfb_create_multi)
   void* blas = nullptr;           // cublasHandle_t, created on first use
   void* solver = nullptr;         // cusolverDnHandle_t, created on first use
 
@@ -139,6 +141,22 @@ int scfb_launch_generate_packed(scfb_handle_s* h, int family, uint64_t seed, con
 void scfb_pack_host(const double* full, int n, int i_lo, int i_hi, double* out);
 // eri_gen.cu
 int scfb_launch_generate_full(scfb_handle_s* h, int family, uint64_t seed, const double* d_aux);
+// scfb_api.cu
+bool scfb_is_pinned(const void* p);
+int scfb_stage_inputs(scfb_handle_s* h, int n_spin, const double* density, const double* total, const double* out);
+int scfb_check_build_args(scfb_handle_s* h, int n_spin, const void* a, const void* b, const void* c);
+int scfb_build_jk(scfb_handle_s* h, int n_spin, const double* d_density, const double* d_total, double* d_out,
+                  cudaEvent_t out_event, const double** jk_final);
+// multi.cu
+void scfb_multi_destroy(scfb_handle_s* h0);
+int scfb_multi_n_dev(scfb_handle_s* h0);
+scfb_handle_s* scfb_multi_member(scfb_handle_s* h0, int g);
+int scfb_multi_sync(scfb_handle_s* h0);
+int scfb_multi_build_dev(scfb_handle_s* h0, int n_spin, const double* d_density, const double* d_total, double* d_out,
+                         cudaEvent_t out_event, const double** jk_final, bool fan_out);
+int scfb_multi_stage_inputs(scfb_handle_s* h0, int n_spin, const double* density, const double* total,
+                            const double* out);
+int scfb_multi_inputs_consumed(scfb_handle_s* h0);
 // comm.cu
 int scfb_comm_allreduce_jk(scfb_handle_s* h, int n_spin);
 int scfb_comm_destroy(scfb_handle_s* h);

@@ -42,7 +42,10 @@ end
 
 """
 J+K builder whose ERI tensor lives in B200 HBM (full fp64 layout or 8-fold packed).
-One builder owns the shard of one GPU: `(rank, n_ranks)` select the nu-slab block.
+`devices=0:7` shards ONE builder over several GPUs of this process (`scfb_create_multi`): the
+unmodified, single-threaded `run_scf` then uses all of them, e.g. for an n_bas = 512 tensor.
+Otherwise one builder owns the shard of one GPU and `(rank, n_ranks)` select the nu-slab block
+(one Julia process per GPU, see `comm_init!`).
 """
 mutable struct JKBuilderCUDA <: TwoElectronBuilder
     handle::Ptr{Cvoid}
@@ -50,12 +53,20 @@ mutable struct JKBuilderCUDA <: TwoElectronBuilder
     layout::Symbol
 
     function JKBuilderCUDA(n_bas::Integer; layout::Symbol=:full, device::Integer=0,
-                           rank::Integer=0, n_ranks::Integer=1)
+                           rank::Integer=0, n_ranks::Integer=1, devices=nothing)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         lay = layout == :full ? SCFB_LAYOUT_FULL : SCFB_LAYOUT_PACKED8
-        check(ccall((:scfb_create, libscf), Cint,
-                    (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint),
-                    h, n_bas, lay, device, rank, n_ranks))
+        if devices === nothing
+            check(ccall((:scfb_create, libscf), Cint,
+                        (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint),
+                        h, n_bas, lay, device, rank, n_ranks))
+        else
+            @assert rank == 0 && n_ranks == 1
+            devs = Cint[d for d in devices]
+            check(ccall((:scfb_create_multi, libscf), Cint,
+                        (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Ptr{Cint}),
+                        h, n_bas, lay, length(devs), devs))
+        end
         obj = new(h[], n_bas, layout)
         finalizer(obj) do b
             b.handle == C_NULL || ccall((:scfb_destroy, libscf), Cint, (Ptr{Cvoid},), b.handle)
@@ -117,8 +128,10 @@ function add_2e_term!(out::AbstractArray, builder::JKBuilderCUDA,
     @assert size(total_density) == (n_bas, n_bas)
     @assert size(density) == (n_bas, n_bas, n_spin)
     @assert n_bas == builder.n_bas
-    d = Array{Float64,3}(density)            # no-op for dense Arrays, copies views
-    t = Array{Float64,2}(total_density)
+    # `convert` returns a dense Array{Float64} argument itself and only copies views / other eltypes
+    # (the `Array{Float64,3}(x)` constructor would copy on every Fock build)
+    d = convert(Array{Float64,3}, density)
+    t = convert(Array{Float64,2}, total_density)
     o = out isa Array{Float64,3} ? out : Array{Float64,3}(out)
     check(ccall((:scfb_fock_jk, libscf), Cint,
                 (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
