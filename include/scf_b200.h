@@ -78,11 +78,13 @@ int scfb_set_stream(scfb_handle_t h, void* cuda_stream);
 /* ---- ERI storage (JKBuilderFromTensor.jl:7-9) -------------------------------------- */
 int scfb_shard_range(scfb_handle_t h, int* nu_lo, int* nu_hi);
 int scfb_eri_bytes(scfb_handle_t h, uint64_t* bytes);
-/* `host_eri` is the FULL n^4 tensor; the handle copies (full layout) or packs (packed8,
- * lower-triangle representatives) what it owns. */
+/* `host_eri` is the FULL n^4 tensor; the handle copies (full layout) or packs on the device
+ * (packed8: representatives eri[k,l,j,i], i >= j, k >= l, pr(i,j) >= pr(k,l)) what it owns. */
 int scfb_eri_upload(scfb_handle_t h, const double* host_eri);
-/* Chunked variant, full layout: `host_slabs` holds nu_count consecutive nu-slabs starting
- * at global slab nu_first; slabs outside the shard are skipped. */
+/* Chunked variant, both layouts: `host_slabs` holds nu_count consecutive nu-slabs eri[:,:,:,nu]
+ * starting at global slab nu_first; slabs outside the shard are skipped.  packed8 packs them on the
+ * device as they arrive (every packed row (i,j) needs nu-slab i only), so neither host nor device
+ * ever holds n^4 doubles (load_integral_hdf5.jl:9-10). */
 int scfb_eri_upload_slabs(scfb_handle_t h, const double* host_slabs, int nu_first, int nu_count);
 /* Declare the shard complete after a sequence of partial scfb_eri_upload_slabs calls.  The handle
  * tracks which owned nu-slabs have arrived: SCFB_ERR_STATE if any is still missing. */
@@ -131,11 +133,12 @@ int scfb_launch_count(scfb_handle_t h, uint64_t* launches);
  * The handle keeps S, h_core, the density, the Fock iterate, the Pulay error, the orbitals
  * and the DIIS history in HBM; per iteration only scalars and DIIS rows cross PCIe.  The
  * caller keeps the control flow of run_scf.jl:21-49 and the <= 6x6 coefficient solves
- * (cDIIS.jl:33-63, EDIIS.jl:20-44).  RHF (restricted, closed shell: 1 spin block) and UHF
- * (2 spin blocks); ROHF is not on the device path. */
+ * (cDIIS.jl:33-63, EDIIS.jl:20-44).  RHF (restricted, closed shell: 1 spin block), UHF (2 spin
+ * blocks) and ROHF (restricted, n_elec_a != n_elec_b: 2 density blocks, ONE Fock / orbital block
+ * — the Roothaan effective Fock of compute_fock_matrix.jl:82-123, built on the device). */
 #define SCFB_GET_FOCK 0      /* the iterate F (after extrapolation)   (n,n,n_spin) */
 #define SCFB_GET_FOCK_NEW 1  /* Fock matrix of the newest build       (n,n,n_spin) */
-#define SCFB_GET_DENSITY 2   /*                                       (n,n,n_spin) */
+#define SCFB_GET_DENSITY 2   /*                                       (n,n,n_densities) */
 #define SCFB_GET_ERROR 3     /* S D F - F D S of the newest build     (n,n,n_spin) */
 #define SCFB_GET_ORBCOEFF 4  /* all n eigenvectors per spin           (n,n,n_spin) */
 #define SCFB_GET_ORBEN 5     /* all n eigenvalues per spin            (n,n_spin)   */
@@ -144,7 +147,8 @@ int scfb_launch_count(scfb_handle_t h, uint64_t* launches);
 #define SCFB_GET_DENSITY_PREV 8  /* convergence (:40 precedes :48)                     */
 int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core, double e_0e,
                    int n_elec_a, int n_elec_b, int n_orb, int restricted, int n_diis_size);
-int scfb_scf_n_spin(scfb_handle_t h, int* n_spin);
+int scfb_scf_n_spin(scfb_handle_t h, int* n_spin);           /* Fock / orbital / error blocks        */
+int scfb_scf_n_densities(scfb_handle_t h, int* n_densities); /* density blocks (compute_density.jl:24-27) */
 int scfb_scf_set_density(scfb_handle_t h, int n_spin, const double* density);
 int scfb_scf_set_fock(scfb_handle_t h, int n_spin, const double* fock);
 /* compute_fock_matrix.jl:8-71 on the resident density: energies4 = {0e, 1e, 2e, total},

@@ -70,10 +70,11 @@ class JKBuilderCUDA(TwoElectronBuilder):
         return self
 
     def upload_slabs(self, slabs, nu_first):
-        """Chunked upload (full layout): `slabs` is (n,n,n,count) holding the nu-slabs
-        nu_first..nu_first+count-1; slabs outside this builder's shard are skipped.  Call
-        `mark_ready()` once the shard is complete (load_integral_hdf5.jl:9-10 TODO: the reference
-        wants to avoid holding the whole tensor in host memory)."""
+        """Chunked upload (both layouts): `slabs` is (n,n,n,count) holding the nu-slabs
+        nu_first..nu_first+count-1; slabs outside this builder's shard are skipped (packed8: the
+        shard is a range of first indices i and row (i,j) is packed on the device from slab i).
+        Call `mark_ready()` once the shard is complete (load_integral_hdf5.jl:9-10 TODO: the
+        reference wants to avoid holding the whole tensor in host memory)."""
         s = capi.as_f64_colmajor(slabs)
         assert s.ndim == 4 and s.shape[:3] == (self.n_bas,) * 3
         capi.check(capi.lib().scfb_eri_upload_slabs(self._h, capi.ptr(s), int(nu_first), s.shape[3]),

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "scfb_launch_count": [_h, C.POINTER(C.c_uint64)],
     "scfb_scf_setup": [_h, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
     "scfb_scf_n_spin": [_h, C.POINTER(C.c_int)],
+    "scfb_scf_n_densities": [_h, C.POINTER(C.c_int)],
     "scfb_scf_set_density": [_h, C.c_int, _dp],
     "scfb_scf_set_fock": [_h, C.c_int, _dp],
     "scfb_scf_fock": [_h, _dp, _dp],

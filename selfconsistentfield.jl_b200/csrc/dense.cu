@@ -19,8 +19,10 @@
 
 struct scfb_scf_state {
   int n = 0, n_orb = 0, n_elec[2] = {0, 0};
-  int n_spin = 1;  // spin blocks of density / Fock (1 = RHF closed shell, 2 = UHF)
+  int n_spin = 1;  // spin blocks of the Fock iterate / orbitals (1 = RHF and ROHF, 2 = UHF)
+  int n_dens = 1;  // spin blocks of the density (compute_density.jl:24-27): 2 for UHF and ROHF
   bool restricted = true;
+  bool rohf = false;  // restricted open shell: 2 densities, Roothaan effective 1-block Fock
   double e0 = 0.0;
   int cap = 5;  // n_diis_size
 
@@ -33,6 +35,16 @@ struct scfb_scf_state {
   double *C = nullptr, *eps = nullptr;                     // 2 n^2, 2 n
   double *Cprev = nullptr, *epsprev = nullptr, *Dprev = nullptr;  // previous Roothaan step
   double *T1 = nullptr, *T2 = nullptr, *Bw = nullptr;      // n^2 scratch
+  double* R = nullptr;       // ROHF scratch: [Pc | Po | Pv | Fc | X | Feff], 6 n^2
+  double* Lchol = nullptr;   // Cholesky factor of S (lower), computed once (ScfProblem.jl:48-49 TODO)
+  int eig_mode = 0;          // 0 = Dsygvd per block (LAPACK path), 1 = cached Cholesky + Dsyevd,
+                             // 2 = cached Cholesky + Jacobi warm-started in the previous step's eigenbasis
+  double* work_ev = nullptr;  // Dsyevd / Dsyevj workspace
+  int lwork_ev = 0;
+  double* Yprev = nullptr;   // 2 n^2: orthonormal eigenvectors of L^-1 F L^-T of the previous step
+  bool have_y[2] = {false, false};
+  int warm_steps[2] = {0, 0};
+  syevjInfo_t jw = nullptr;
   double *work = nullptr;
   int lwork = 0;
   syevjInfo_t jacobi = nullptr;  // SCFB_EIG=jacobi: cusolverDnDsygvj instead of Dsygvd
@@ -52,6 +64,7 @@ struct scfb_scf_state {
 namespace {
 
 constexpr int kScal = 64;
+
 
 #define SCFB_BLAS(h, call)                                                                  \
   do {                                                                                      \
@@ -150,6 +163,29 @@ __global__ void fock_add_kernel(const double* __restrict__ G, const double* __re
     F[i] = G[i] + H[i % n2];
 }
 
+// ROHF projector pieces (compute_fock_matrix.jl:105-110): Fc = (Fa + Fb)/2, Dab = Da - Db
+__global__ void rohf_prepare_kernel(const double* __restrict__ F2, const double* __restrict__ D2,
+                                    double* __restrict__ Fc, double* __restrict__ Dab, size_t n2) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    Fc[i] = (F2[i] + F2[n2 + i]) / 2;
+    Dab[i] = D2[i] - D2[n2 + i];
+  }
+}
+// Pv = I - Da S  given  Pv = Da S
+__global__ void one_minus_kernel(double* __restrict__ P, int n) {
+  const size_t n2 = (size_t)n * n;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
+    P[i] = (i % n == i / n ? 1.0 : 0.0) - P[i];
+}
+// out = A + A'   (compute_fock_matrix.jl:122)
+__global__ void add_transpose_kernel(const double* __restrict__ A, double* __restrict__ out, int n) {
+  const size_t n2 = (size_t)n * n;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n2; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = e % n, j = e / n;
+    out[e] = A[e] + A[j + i * n];
+  }
+}
+
 struct LinComb {
   const double* m[kMaxPairs];
   int count;
@@ -187,6 +223,108 @@ int pulay_block(scfb_handle_s* h, scfb_scf_state* st, const double* F, const dou
   return gemm(h, st, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, -1.0, F, n, st->T2, n, 1.0, E, n);
 }
 
+// Roothaan effective Fock (compute_fock_matrix.jl:82-123) on resident matrices: F2 = (Fa, Fb),
+// D2 = (Da, Db) -> Feff (one block).  Same association as the reference's expression:
+//   Feff = Pc' Fc Pc / 2 + Po' Fb Pc + Po' Fc Po / 2 + Pv' Fc Pc + Pv' Fa Po + Pv' Fc Pv / 2;  result Feff + Feff'
+int rohf_effective_fock(scfb_handle_s* h, scfb_scf_state* st, const double* F2, const double* D2, double* out) {
+  const int n = st->n;
+  const size_t n2 = (size_t)n * n;
+  double *Pc = st->R, *Po = st->R + n2, *Pv = st->R + 2 * n2, *Fc = st->R + 3 * n2, *X = st->R + 4 * n2,
+         *Fe = st->R + 5 * n2;
+  const double *Fa = F2, *Fb = F2 + n2, *Da = D2, *Db = D2 + n2;
+  rohf_prepare_kernel<<<blocks_for(n2), 256, 0, h->stream>>>(F2, D2, Fc, st->T1, n2);  // T1 = Da - Db
+  h->launches += 1;
+  auto mm = [&](cublasOperation_t ta, double alpha, const double* A, const double* B, double beta, double* Cm) {
+    return gemm(h, st, ta, CUBLAS_OP_N, n, n, n, alpha, A, n, B, n, beta, Cm, n);
+  };
+  if (int rc = mm(CUBLAS_OP_N, 1.0, Db, st->S, 0.0, Pc)) return rc;      // Pc = Db S
+  if (int rc = mm(CUBLAS_OP_N, 1.0, st->T1, st->S, 0.0, Po)) return rc;  // Po = (Da - Db) S
+  if (int rc = mm(CUBLAS_OP_N, 1.0, Da, st->S, 0.0, Pv)) return rc;      // Pv = I - Da S
+  one_minus_kernel<<<blocks_for(n2), 256, 0, h->stream>>>(Pv, n);
+  h->launches += 1;
+  if (int rc = mm(CUBLAS_OP_N, 1.0, Fc, Pc, 0.0, X)) return rc;   // X = Fc Pc
+  if (int rc = mm(CUBLAS_OP_T, 0.5, Pc, X, 0.0, Fe)) return rc;   //   Pc' Fc Pc / 2
+  if (int rc = mm(CUBLAS_OP_T, 1.0, Pv, X, 1.0, Fe)) return rc;   // + Pv' Fc Pc
+  if (int rc = mm(CUBLAS_OP_N, 1.0, Fb, Pc, 0.0, X)) return rc;   // X = Fb Pc
+  if (int rc = mm(CUBLAS_OP_T, 1.0, Po, X, 1.0, Fe)) return rc;   // + Po' Fb Pc
+  if (int rc = mm(CUBLAS_OP_N, 1.0, Fc, Po, 0.0, X)) return rc;   // X = Fc Po
+  if (int rc = mm(CUBLAS_OP_T, 0.5, Po, X, 1.0, Fe)) return rc;   // + Po' Fc Po / 2
+  if (int rc = mm(CUBLAS_OP_N, 1.0, Fa, Po, 0.0, X)) return rc;   // X = Fa Po
+  if (int rc = mm(CUBLAS_OP_T, 1.0, Pv, X, 1.0, Fe)) return rc;   // + Pv' Fa Po
+  if (int rc = mm(CUBLAS_OP_N, 1.0, Fc, Pv, 0.0, X)) return rc;   // X = Fc Pv
+  if (int rc = mm(CUBLAS_OP_T, 0.5, Pv, X, 1.0, Fe)) return rc;   // + Pv' Fc Pv / 2
+  add_transpose_kernel<<<blocks_for(n2), 256, 0, h->stream>>>(Fe, out, n);
+  h->launches += 1;
+  return SCFB_OK;
+}
+
+// Orbitals of the iterate F (n_spin blocks) into st->C / st->eps (compute_orbitals.jl:14): LAPACK
+// sygvd semantics (C' S C = I, ascending eps).  eig_mode 0: cusolverDnDsygvd per block.  eig_mode
+// 1/2: S = L L' was factored once at setup, so a block costs A = L^-1 F L^-T (two Dtrsm), a
+// standard symmetric eigensolve (Dsyevd per block, or ONE batched syev for both spin blocks) and
+// C = L^-T Y (one Dtrsm).
+int solve_orbitals(scfb_handle_s* h, scfb_scf_state* st) {
+  const int n = st->n, ns = st->n_spin;
+  const size_t n2 = (size_t)n * n;
+  if (st->eig_mode == 0) {
+    for (int s = 0; s < ns; ++s) {
+      double* Cs = st->C + s * n2;
+      SCFB_CUDA(h, cudaMemcpyAsync(Cs, st->F + s * n2, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      SCFB_CUDA(h, cudaMemcpyAsync(st->Bw, st->S, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      if (st->jacobi)
+        SCFB_SOLVER(h, cusolverDnDsygvj(st->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
+                                        CUBLAS_FILL_MODE_LOWER, n, Cs, n, st->Bw, n, st->eps + s * n,
+                                        st->work_j, st->lwork_j, st->dev_info, st->jacobi));
+      else
+        SCFB_SOLVER(h, cusolverDnDsygvd(st->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
+                                        CUBLAS_FILL_MODE_LOWER, n, Cs, n, st->Bw, n, st->eps + s * n,
+                                        st->work, st->lwork, st->dev_info));
+      h->launches += 1;
+    }
+    return SCFB_OK;
+  }
+  const double one = 1.0;
+  SCFB_CUDA(h, cudaMemcpyAsync(st->C, st->F, n2 * ns * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  for (int s = 0; s < ns; ++s) {
+    double* A = st->C + s * n2;
+    SCFB_BLAS(h, cublasDtrsm(st->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT,
+                             n, n, &one, st->Lchol, n, A, n));  // A <- L^-1 F
+    SCFB_BLAS(h, cublasDtrsm(st->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
+                             n, n, &one, st->Lchol, n, A, n));  // A <- A L^-T
+    h->launches += 2;
+    if (st->eig_mode == 1) {
+      SCFB_SOLVER(h, cusolverDnDsyevd(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, A, n,
+                                      st->eps + s * n, st->work_ev, st->lwork_ev, st->dev_info));
+      h->launches += 1;
+    } else {
+      // The iterate changes little from one SCF step to the next: in the previous step's eigenbasis
+      // it is nearly diagonal and the cyclic Jacobi method converges in a few sweeps.
+      double* Yp = st->Yprev + s * n2;
+      if (++st->warm_steps[s] % 16 == 0) st->have_y[s] = false;  // periodic cold solve: Y = Yp V V' ... stays orthonormal
+      if (st->have_y[s]) {
+        if (int rc = gemm(h, st, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, 1.0, A, n, Yp, n, 0.0, st->T1, n)) return rc;
+        if (int rc = gemm(h, st, CUBLAS_OP_T, CUBLAS_OP_N, n, n, n, 1.0, Yp, n, st->T1, n, 0.0, st->T2, n)) return rc;
+      } else {
+        SCFB_CUDA(h, cudaMemcpyAsync(st->T2, A, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      }
+      SCFB_SOLVER(h, cusolverDnDsyevj(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, st->T2, n,
+                                      st->eps + s * n, st->work_ev, st->lwork_ev, st->dev_info, st->jw));
+      h->launches += 1;
+      if (st->have_y[s]) {
+        if (int rc = gemm(h, st, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, 1.0, Yp, n, st->T2, n, 0.0, A, n)) return rc;  // Y = Yp V
+      } else {
+        SCFB_CUDA(h, cudaMemcpyAsync(A, st->T2, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      }
+      SCFB_CUDA(h, cudaMemcpyAsync(Yp, A, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      st->have_y[s] = true;
+    }
+    SCFB_BLAS(h, cublasDtrsm(st->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, n,
+                             n, &one, st->Lchol, n, A, n));  // C <- L^-T Y
+    h->launches += 1;
+  }
+  return SCFB_OK;
+}
+
 int ensure_dense_handles(scfb_handle_s* h) {
   if (!h->blas) {
     cublasHandle_t b = nullptr;
@@ -220,8 +358,9 @@ void scfb_scf_free(scfb_handle_s* h) {
   if (!st) return;
   for (double* p : {st->S, st->H, st->F, st->Fnew, st->D, st->Dtot, st->G, st->E, st->C, st->eps,
                     st->T1, st->T2, st->Bw, st->work, st->scal, st->coef, st->Fh, st->Eh, st->Dh,
-                    st->Cprev, st->epsprev, st->Dprev})
+                    st->Cprev, st->epsprev, st->Dprev, st->R, st->Lchol, st->work_ev, st->Yprev})
     cudaFree(p);
+  if (st->jw) cusolverDnDestroySyevjInfo(st->jw);
   cudaFree(st->dev_info);
   cudaFree(st->work_j);
   if (st->jacobi) cusolverDnDestroySyevjInfo(st->jacobi);
@@ -250,9 +389,6 @@ int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core,
                "n_elec of alpha and beta should be less than n_orb");
   SCFB_REQUIRE(h, n_diis_size >= 1 && n_diis_size <= kMaxPairs, "n_diis_size must be in [1, %d]",
                kMaxPairs);
-  SCFB_REQUIRE(h, !(restricted && n_elec_a != n_elec_b),
-               "restricted open-shell (ROHF effective Fock, compute_fock_matrix.jl:82-123) is not "
-               "on the device path; use restricted=false or the host path");
   SCFB_CUDA(h, cudaSetDevice(h->device));
   scfb_scf_free(h);
   scfb_scf_state* st = new scfb_scf_state();
@@ -262,7 +398,9 @@ int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core,
   st->n_elec[0] = n_elec_a;
   st->n_elec[1] = n_elec_b;
   st->restricted = restricted != 0;
-  st->n_spin = st->restricted ? 1 : 2;  // compute_density.jl:24-27
+  st->n_spin = st->restricted ? 1 : 2;
+  st->rohf = st->restricted && n_elec_a != n_elec_b;
+  st->n_dens = (!st->restricted || st->rohf) ? 2 : 1;  // compute_density.jl:24-27
   st->e0 = e_0e;
   st->cap = n_diis_size;
   const size_t n2 = (size_t)n * n;
@@ -299,18 +437,48 @@ int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core,
                                              CUBLAS_FILL_MODE_LOWER, n, st->T1, n, st->Bw, n, st->eps,
                                              &st->lwork));
   SCFB_CUDA(h, alloc(&st->work, st->lwork > 0 ? st->lwork : 1));
-  if (const char* eig = std::getenv("SCFB_EIG"); eig && std::strcmp(eig, "jacobi") == 0) {
-    SCFB_SOLVER(h, cusolverDnCreateSyevjInfo(&st->jacobi));
-    SCFB_SOLVER(h, cusolverDnXsyevjSetTolerance(st->jacobi, 1e-15));
-    SCFB_SOLVER(h, cusolverDnXsyevjSetMaxSweeps(st->jacobi, 100));
-    SCFB_SOLVER(h, cusolverDnXsyevjSetSortEig(st->jacobi, 1));
-    SCFB_SOLVER(h, cusolverDnDsygvj_bufferSize(st->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
-                                               CUBLAS_FILL_MODE_LOWER, n, st->T1, n, st->Bw, n, st->eps,
-                                               &st->lwork_j, st->jacobi));
-    SCFB_CUDA(h, alloc(&st->work_j, st->lwork_j > 0 ? st->lwork_j : 1));
+  if (st->rohf) SCFB_CUDA(h, alloc(&st->R, 6 * n2));
+  // eigensolver: SCFB_EIG = sygvd | syevd | warm | jacobi (see solve_orbitals)
+  {
+    const char* eig = std::getenv("SCFB_EIG");
+    // default (same-box timings in profiles/README.md): the warm-started Jacobi wins while the matrices are
+    // small (n_bf = 128: 2.9 vs 3.6 ms per RHF iteration, 3.1 vs 5.6 UHF), Dsyevd on the cached factor beyond
+    st->eig_mode = !eig ? (n < 200 ? 2 : 1)
+                        : (std::strcmp(eig, "syevd") == 0 ? 1 : (std::strcmp(eig, "warm") == 0 ? 2 : 0));
+  }
+  if (st->eig_mode != 0) {
+    SCFB_CUDA(h, alloc(&st->Lchol, n2));
+    if (st->eig_mode == 1) {
+      SCFB_SOLVER(h, cusolverDnDsyevd_bufferSize(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
+                                                 st->T1, n, st->eps, &st->lwork_ev));
+    } else {
+      SCFB_CUDA(h, alloc(&st->Yprev, 2 * n2));
+      SCFB_SOLVER(h, cusolverDnCreateSyevjInfo(&st->jw));
+      SCFB_SOLVER(h, cusolverDnXsyevjSetTolerance(st->jw, 1e-15));
+      SCFB_SOLVER(h, cusolverDnXsyevjSetMaxSweeps(st->jw, 100));
+      SCFB_SOLVER(h, cusolverDnXsyevjSetSortEig(st->jw, 1));
+      SCFB_SOLVER(h, cusolverDnDsyevj_bufferSize(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
+                                                 st->T1, n, st->eps, &st->lwork_ev, st->jw));
+    }
+    SCFB_CUDA(h, alloc(&st->work_ev, st->lwork_ev > 0 ? st->lwork_ev : 1));
   }
   SCFB_CUDA(h, cudaMemcpyAsync(st->S, overlap, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   SCFB_CUDA(h, cudaMemcpyAsync(st->H, h_core, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (st->eig_mode != 0) {  // S = L L' once: the overlap is constant over the SCF (ScfProblem.jl:48-49)
+    SCFB_CUDA(h, cudaMemcpyAsync(st->Lchol, st->S, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    int lw = 0;
+    SCFB_SOLVER(h, cusolverDnDpotrf_bufferSize(st->solver, CUBLAS_FILL_MODE_LOWER, n, st->Lchol, n, &lw));
+    double* w = nullptr;
+    SCFB_CUDA(h, cudaMalloc(&w, (lw > 0 ? lw : 1) * sizeof(double)));
+    cusolverStatus_t cs = cusolverDnDpotrf(st->solver, CUBLAS_FILL_MODE_LOWER, n, st->Lchol, n, w, lw, st->dev_info);
+    int info = 0;
+    cudaMemcpyAsync(&info, st->dev_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t ce = cudaStreamSynchronize(h->stream);
+    cudaFree(w);
+    if (cs != CUSOLVER_STATUS_SUCCESS || ce != cudaSuccess || info != 0)
+      return scfb_fail(h, SCFB_ERR_CUSOLVER, "Cholesky factorisation of the overlap failed (info=%d): S must be "
+                       "symmetric positive definite", info);
+  }
   if (int rc_ = scfb_stream_sync_checked(h)) return rc_;
   return SCFB_OK;
 }
@@ -321,12 +489,18 @@ int scfb_scf_n_spin(scfb_handle_t h, int* n_spin) {
   return SCFB_OK;
 }
 
+int scfb_scf_n_densities(scfb_handle_t h, int* n_densities) {
+  if (int rc = require_state(h)) return rc;
+  if (n_densities) *n_densities = h->scf->n_dens;
+  return SCFB_OK;
+}
+
 int scfb_scf_set_density(scfb_handle_t h, int n_spin, const double* density) {
   if (int rc = require_state(h)) return rc;
   scfb_scf_state* st = h->scf;
   SCFB_REQUIRE(h, density, "null density");
-  SCFB_REQUIRE(h, n_spin == st->n_spin, "density has %d spin blocks, problem needs %d", n_spin,
-               st->n_spin);
+  SCFB_REQUIRE(h, n_spin == st->n_dens, "density has %d spin blocks, problem needs %d", n_spin,
+               st->n_dens);
   const size_t n2 = (size_t)st->n * st->n;
   SCFB_CUDA(h, cudaMemcpyAsync(st->D, density, n2 * n_spin * sizeof(double), cudaMemcpyHostToDevice,
                                h->stream));
@@ -353,21 +527,30 @@ int scfb_scf_fock(scfb_handle_t h, double* energies4, double* error_norm) {
   if (int rc = require_state(h)) return rc;
   scfb_scf_state* st = h->scf;
   if (!st->have_density) return scfb_fail(h, SCFB_ERR_STATE, "no density: call scfb_scf_set_density");
-  const int n = st->n, ns = st->n_spin;
+  const int n = st->n, ns = st->n_spin, nd = st->n_dens;
   const size_t n2 = (size_t)n * n;
-  prepare_build_kernel<<<blocks_for(n2), 256, 0, h->stream>>>(st->D, st->Dtot, st->G, n2, ns);
+  prepare_build_kernel<<<blocks_for(n2), 256, 0, h->stream>>>(st->D, st->Dtot, st->G, n2, nd);
   h->launches += 1;
-  if (int rc = scfb_fock_jk_dev(h, ns, st->D, st->Dtot, st->G)) return rc;
-  fock_add_kernel<<<blocks_for(n2 * ns), 256, 0, h->stream>>>(st->G, st->H, st->Fnew, n2, ns);
-  h->launches += 1;
-  for (int s = 0; s < ns; ++s)
-    if (int rc = pulay_block(h, st, st->Fnew + s * n2, st->D + s * n2, st->E + s * n2)) return rc;
+  if (int rc = scfb_fock_jk_dev(h, nd, st->D, st->Dtot, st->G)) return rc;
+  if (st->rohf) {
+    // compute_fock_matrix.jl:58-65: the two-block G + h_core goes through the Roothaan effective
+    // Fock; the Pulay error is that of the effective Fock with the TOTAL density (one block)
+    fock_add_kernel<<<blocks_for(n2 * 2), 256, 0, h->stream>>>(st->G, st->H, st->E, n2, 2);  // E = scratch (Fa, Fb)
+    h->launches += 1;
+    if (int rc = rohf_effective_fock(h, st, st->E, st->D, st->Fnew)) return rc;
+    if (int rc = pulay_block(h, st, st->Fnew, st->Dtot, st->E)) return rc;
+  } else {
+    fock_add_kernel<<<blocks_for(n2 * ns), 256, 0, h->stream>>>(st->G, st->H, st->Fnew, n2, ns);
+    h->launches += 1;
+    for (int s = 0; s < ns; ++s)
+      if (int rc = pulay_block(h, st, st->Fnew + s * n2, st->D + s * n2, st->E + s * n2)) return rc;
+  }
   // scalars: [0] tr(h Dtot)  [1],[2] tr(G_s D_s)  [3],[4] <E_s, E_s>
   TraceBatch tb{};
   int k = 0;
   tb.p[k++] = {st->H, st->Dtot, 1};
   for (int s = 0; s < 2; ++s) {
-    const int ss = s < ns ? s : 0;
+    const int ss = s < nd ? s : 0;
     tb.p[k++] = {st->G + ss * n2, st->D + ss * n2, 1};
   }
   for (int s = 0; s < 2; ++s) {
@@ -382,7 +565,7 @@ int scfb_scf_fock(scfb_handle_t h, double* energies4, double* error_norm) {
   if (int rc_ = scfb_stream_sync_checked(h)) return rc_;
   const double* v = st->h_scal;
   const double e1 = v[0];
-  const double e2 = ns == 1 ? v[1] : 0.5 * (v[1] + v[2]);  // compute_fock_matrix.jl:44-53
+  const double e2 = nd == 1 ? v[1] : 0.5 * (v[1] + v[2]);  // compute_fock_matrix.jl:44-53
   if (energies4) {
     energies4[0] = st->e0;
     energies4[1] = e1;
@@ -398,39 +581,26 @@ int scfb_scf_roothaan(scfb_handle_t h) {
   if (int rc = require_state(h)) return rc;
   scfb_scf_state* st = h->scf;
   if (!st->have_fock) return scfb_fail(h, SCFB_ERR_STATE, "no Fock iterate on the device");
-  const int n = st->n, ns = st->n_spin;
+  const int n = st->n, ns = st->n_spin, nd = st->n_dens;
   const size_t n2 = (size_t)n * n;
   // keep the previous step's orbitals/density: run_scf.jl:52-58 returns those on convergence
   SCFB_CUDA(h, cudaMemcpyAsync(st->Cprev, st->C, 2 * n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   SCFB_CUDA(h, cudaMemcpyAsync(st->epsprev, st->eps, 2 * (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   SCFB_CUDA(h, cudaMemcpyAsync(st->Dprev, st->D, 2 * n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  for (int s = 0; s < ns; ++s) {
-    double* Cs = st->C + s * n2;
-    SCFB_CUDA(h, cudaMemcpyAsync(Cs, st->F + s * n2, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    SCFB_CUDA(h, cudaMemcpyAsync(st->Bw, st->S, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    if (st->jacobi)
-      SCFB_SOLVER(h, cusolverDnDsygvj(st->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
-                                      CUBLAS_FILL_MODE_LOWER, n, Cs, n, st->Bw, n, st->eps + s * n,
-                                      st->work_j, st->lwork_j, st->dev_info, st->jacobi));
-    else
-      SCFB_SOLVER(h, cusolverDnDsygvd(st->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
-                                      CUBLAS_FILL_MODE_LOWER, n, Cs, n, st->Bw, n, st->eps + s * n,
-                                      st->work, st->lwork, st->dev_info));
-    h->launches += 1;
-  }
+  if (int rc = solve_orbitals(h, st)) return rc;
   int info = 0;
   SCFB_CUDA(h, cudaMemcpyAsync(&info, st->dev_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (int rc_ = scfb_stream_sync_checked(h)) return rc_;
-  if (info != 0) return scfb_fail(h, SCFB_ERR_CUSOLVER, "Dsygvd failed: info=%d", info);
-  // D_s = C[:, 1:n_elec[s], s'] C[...]'   (compute_density.jl:16-32)
-  for (int s = 0; s < ns; ++s) {
+  if (info != 0) return scfb_fail(h, SCFB_ERR_CUSOLVER, "eigensolver failed: info=%d", info);
+  // D_s = C[:, 1:n_elec[s], s'] C[...]'   (compute_density.jl:16-32; ROHF: both densities from the one orbital block)
+  for (int s = 0; s < nd; ++s) {
     const int nocc = st->n_elec[s];
     double* Ds = st->D + s * n2;
     if (nocc == 0) {
       SCFB_CUDA(h, cudaMemsetAsync(Ds, 0, n2 * sizeof(double), h->stream));
       continue;
     }
-    const double* Cs = st->C + s * n2;
+    const double* Cs = st->C + (s < ns ? s : ns - 1) * n2;
     if (int rc = gemm(h, st, CUBLAS_OP_N, CUBLAS_OP_T, n, n, nocc, 1.0, Cs, n, Cs, n, 0.0, Ds, n)) return rc;
   }
   st->have_density = true;
@@ -556,13 +726,13 @@ int scfb_scf_get(scfb_handle_t h, int what, double* host_out) {
   switch (what) {
     case SCFB_GET_FOCK: src = st->F; count = n2 * ns; break;
     case SCFB_GET_FOCK_NEW: src = st->Fnew; count = n2 * ns; break;
-    case SCFB_GET_DENSITY: src = st->D; count = n2 * ns; break;
+    case SCFB_GET_DENSITY: src = st->D; count = n2 * st->n_dens; break;
     case SCFB_GET_ERROR: src = st->E; count = n2 * ns; break;
     case SCFB_GET_ORBCOEFF: src = st->C; count = n2 * ns; break;  // all n columns per spin
     case SCFB_GET_ORBEN: src = st->eps; count = n * ns; break;
     case SCFB_GET_ORBCOEFF_PREV: src = st->Cprev; count = n2 * ns; break;
     case SCFB_GET_ORBEN_PREV: src = st->epsprev; count = n * ns; break;
-    case SCFB_GET_DENSITY_PREV: src = st->Dprev; count = n2 * ns; break;
+    case SCFB_GET_DENSITY_PREV: src = st->Dprev; count = n2 * st->n_dens; break;
     default: return scfb_fail(h, SCFB_ERR_ARG, "unknown quantity %d", what);
   }
   SCFB_CUDA(h, cudaMemcpyAsync(host_out, src, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -597,6 +597,46 @@ __global__ void generate_packed_kernel(double* __restrict__ eri, const uint64_t*
   }
 }
 
+// K3b — pack uploaded nu-slabs into the packed8 shard (load_integral_hdf5.jl:9-10: the tensor never
+// has to exist as a whole, neither on the host nor on the device).  Slab i of the Julia-ordered tensor
+// is X[a,b,c] = eri[a,b,c,i] = (ab|ci); by the 8-fold symmetry (ij|kl) = (kl|ji) = X[k,l,j], so every
+// packed row (i,j), j <= i, comes from slab nu = i alone: out[R(i,j) + E(k) + l] = f * X[k + n l + n^2 j].
+// One CTA = one 32x32 (k,l) tile of one (slab, j): read coalesced along k, transposed through shared
+// memory, written coalesced along l — pre-scaled and with the segment pads zeroed.
+__global__ void __launch_bounds__(256) pack_slabs_kernel(const double* __restrict__ slabs, int i_first,
+                                                        double* __restrict__ eri, const uint64_t* __restrict__ Btab,
+                                                        uint64_t shard_offset, int n, int n_tiles) {
+  __shared__ double tile[32][33];
+  const int i = i_first + blockIdx.z, j = blockIdx.y;
+  if (j > i) return;
+  const int kt = blockIdx.x / n_tiles, lt = blockIdx.x % n_tiles;
+  const int k0 = kt * 32, l0 = lt * 32;
+  if (k0 > i || l0 > k0 + 31) return;  // beyond the last segment / above the triangle (incl. its pad)
+  const double* X = slabs + (size_t)blockIdx.z * n * n * n + (size_t)j * n * n;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {  // tile[l - l0][k - k0]
+    const int k = k0 + tx, l = l0 + r;
+    tile[r][tx] = (k < n && l < n) ? X[k + (size_t)n * l] : 0.0;
+  }
+  __syncthreads();
+  double* row = eri + (Btab[i] + (uint64_t)j * seg_off(i) + seg_off(j) - shard_offset);
+  const uint64_t p = tri(i) + j;
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, l = l0 + tx;
+    if (k > i) continue;
+    const int lmax = k < i ? k : j;
+    if (l >= (int)seg_len(lmax + 1)) continue;
+    double v = 0.0;
+    if (l <= lmax) {
+      v = tile[tx][r];
+      if (i == j) v *= 0.5;
+      if (k == l) v *= 0.5;
+      if (p == tri(k) + l) v *= 0.5;
+    }
+    row[seg_off(k) + l] = v;
+  }
+}
+
 }  // namespace
 
 // ---- host side -------------------------------------------------------------------------
@@ -744,26 +784,13 @@ int scfb_launch_generate_packed(scfb_handle_s* h, int family, uint64_t seed, con
   return SCFB_OK;
 }
 
-// Host-side packing of this rank's rows from a full column-major tensor (small n: the full
-// tensor exists on the host anyway).  Representative of each orbit: eri[i,j,k,l] with
-// i>=j, k>=l, pr(i,j) >= pr(k,l).  `out` must hold B[i_hi] - B[i_lo] doubles.
-void scfb_pack_host(const double* full, int n, int i_lo, int i_hi, double* out) {
-  const uint64_t N = n;
-  uint64_t pos = 0;
-  for (uint64_t i = i_lo; i < (uint64_t)i_hi; ++i)
-    for (uint64_t j = 0; j <= i; ++j) {
-      const uint64_t p = tri(i) + j;
-      for (uint64_t k = 0; k <= i; ++k) {
-        const uint64_t lmax = k < i ? k : j;
-        for (uint64_t l = 0; l <= lmax; ++l) {
-          const uint64_t q = tri(k) + l;
-          double v = full[i + N * (j + N * (k + N * l))];
-          if (i == j) v *= 0.5;
-          if (k == l) v *= 0.5;
-          if (p == q) v *= 0.5;
-          out[pos++] = v;
-        }
-        for (uint64_t l = lmax + 1; l < seg_len(lmax + 1); ++l) out[pos++] = 0.0;  // pad the segment
-      }
-    }
+// Pack `count` consecutive nu-slabs (device memory, slab i_first first) into the shard.
+int scfb_launch_pack_slabs(scfb_handle_s* h, const double* d_slabs, int i_first, int count) {
+  const int n_tiles = (h->n + 31) / 32;
+  dim3 grid(n_tiles * n_tiles, i_first + count, count);  // (tile, j, slab); j > i exits at once
+  pack_slabs_kernel<<<grid, 256, 0, h->stream>>>(d_slabs, i_first, h->eri, h->pk_btab, h->pk_offset, h->n, n_tiles);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "pack_slabs_kernel launch: %s", cudaGetErrorString(e));
+  h->launches += 1;
+  return SCFB_OK;
 }

@@ -245,6 +245,7 @@ int scfb_destroy(scfb_handle_t h) {
   cudaFree(h->pk_dq2);
   cudaFree(h->pk_dpad);
   cudaFree(h->pk_btab);
+  cudaFree(h->pack_stage);
   for (auto* p : h->pk_items) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   std::free(h->slab_seen);
@@ -299,45 +300,51 @@ int scfb_eri_bytes(scfb_handle_t h, uint64_t* bytes) {
 static int one_eri_upload_slabs(scfb_handle_t h, const double* host_slabs, int nu_first, int nu_count) {
   if (int rc = check_handle(h)) return rc;
   SCFB_REQUIRE(h, host_slabs, "null host pointer");
-  SCFB_REQUIRE(h, h->layout == SCFB_LAYOUT_FULL, "slab upload is for the full layout; use scfb_eri_upload");
   SCFB_REQUIRE(h, nu_first >= 0 && nu_count >= 0 && nu_first + nu_count <= h->n,
                "slab range [%d, %d) outside [0, %d)", nu_first, nu_first + nu_count, h->n);
-  const int lo = nu_first > h->nu_lo ? nu_first : h->nu_lo;
-  const int hi = nu_first + nu_count < h->nu_hi ? nu_first + nu_count : h->nu_hi;
+  const bool full = h->layout == SCFB_LAYOUT_FULL;
+  const int own_lo = full ? h->nu_lo : h->i_lo, own_hi = full ? h->nu_hi : h->i_hi;
+  const int lo = nu_first > own_lo ? nu_first : own_lo;
+  const int hi = nu_first + nu_count < own_hi ? nu_first + nu_count : own_hi;
   if (hi > lo) {
     if (!h->slab_seen) {
       h->slab_seen = static_cast<uint64_t*>(std::calloc((h->n + 63) / 64, sizeof(uint64_t)));
       if (!h->slab_seen) return scfb_fail(h, SCFB_ERR_OOM, "host allocation failed");
     }
     const uint64_t n3 = (uint64_t)h->n * h->n * h->n;
-    SCFB_CUDA(h, cudaMemcpyAsync(h->eri + (uint64_t)(lo - h->nu_lo) * n3,
-                                 host_slabs + (uint64_t)(lo - nu_first) * n3,
-                                 (uint64_t)(hi - lo) * n3 * sizeof(double), cudaMemcpyHostToDevice,
-                                 h->stream));
+    if (full) {
+      SCFB_CUDA(h, cudaMemcpyAsync(h->eri + (uint64_t)(lo - h->nu_lo) * n3,
+                                   host_slabs + (uint64_t)(lo - nu_first) * n3,
+                                   (uint64_t)(hi - lo) * n3 * sizeof(double), cudaMemcpyHostToDevice,
+                                   h->stream));
+    } else {
+      // packed8: every row (i, j <= i) of the shard comes from nu-slab i alone (8-fold symmetry), so
+      // the owned slabs pass through a bounded device staging buffer and are packed there
+      size_t batch = (size_t)(256u << 20) / (n3 * sizeof(double));
+      if (batch < 1) batch = 1;
+      if (batch > (size_t)(hi - lo)) batch = hi - lo;
+      if (h->pack_stage_slabs < batch) {
+        cudaFree(h->pack_stage);
+        h->pack_stage = nullptr;
+        h->pack_stage_slabs = 0;
+        SCFB_CUDA(h, cudaMalloc(&h->pack_stage, batch * n3 * sizeof(double)));
+        h->pack_stage_slabs = batch;
+      }
+      for (int v = lo; v < hi; v += (int)batch) {
+        const int cnt = v + (int)batch < hi ? (int)batch : hi - v;
+        SCFB_CUDA(h, cudaMemcpyAsync(h->pack_stage, host_slabs + (uint64_t)(v - nu_first) * n3,
+                                     (uint64_t)cnt * n3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (int rc = scfb_launch_pack_slabs(h, h->pack_stage, v, cnt)) return rc;
+      }
+    }
     SCFB_CUDA(h, cudaStreamSynchronize(h->stream));
     for (int v = lo; v < hi; ++v) h->slab_seen[v >> 6] |= 1ull << (v & 63);
   }
-  if (lo <= h->nu_lo && hi >= h->nu_hi) h->eri_ready = true;  // whole shard arrived in one call
+  if (lo <= own_lo && hi >= own_hi) h->eri_ready = true;  // whole shard arrived in one call
   return SCFB_OK;
 }
 
 static int one_eri_upload(scfb_handle_t h, const double* host_eri) {
-  if (h && h->layout == SCFB_LAYOUT_PACKED8) {
-    if (int rc = check_handle(h)) return rc;
-    SCFB_REQUIRE(h, host_eri, "null host pointer");
-    if (h->eri_elems) {
-      double* tmp = static_cast<double*>(std::malloc(h->eri_elems * sizeof(double)));
-      if (!tmp) return scfb_fail(h, SCFB_ERR_OOM, "host packing buffer allocation failed");
-      scfb_pack_host(host_eri, h->n, h->i_lo, h->i_hi, tmp);
-      cudaError_t e = cudaMemcpyAsync(h->eri, tmp, h->eri_elems * sizeof(double),
-                                      cudaMemcpyHostToDevice, h->stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-      std::free(tmp);
-      if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "packed upload: %s", cudaGetErrorString(e));
-    }
-    h->eri_ready = true;
-    return SCFB_OK;
-  }
   int rc = one_eri_upload_slabs(h, host_eri, 0, h ? h->n : 0);
   if (rc == SCFB_OK) h->eri_ready = true;
   return rc;
@@ -346,13 +353,14 @@ static int one_eri_upload(scfb_handle_t h, const double* host_eri) {
 static int one_eri_mark_ready(scfb_handle_t h) {  // after a sequence of partial slab uploads
   if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
   if (h->eri_ready) return SCFB_OK;
-  if (h->layout == SCFB_LAYOUT_FULL)
-    for (int v = h->nu_lo; v < h->nu_hi; ++v)
-      if (!h->slab_seen || !(h->slab_seen[v >> 6] >> (v & 63) & 1))
-        return scfb_fail(h, SCFB_ERR_STATE, "nu-slab %d of the shard [%d, %d) was never uploaded", v, h->nu_lo,
-                         h->nu_hi);
-  if (h->layout == SCFB_LAYOUT_PACKED8 && h->eri_elems && !h->pk_rows_seen_all)
-    return scfb_fail(h, SCFB_ERR_STATE, "packed shard incomplete: not every owned row block was streamed in");
+  const bool full = h->layout == SCFB_LAYOUT_FULL;
+  const int own_lo = full ? h->nu_lo : h->i_lo, own_hi = full ? h->nu_hi : h->i_hi;
+  for (int v = own_lo; v < own_hi; ++v)
+    if (!h->slab_seen || !(h->slab_seen[v >> 6] >> (v & 63) & 1))
+      return scfb_fail(h, SCFB_ERR_STATE, "nu-slab %d of the shard [%d, %d) was never uploaded", v, own_lo, own_hi);
+  cudaFree(h->pack_stage);  // the staging buffer is only needed while loading
+  h->pack_stage = nullptr;
+  h->pack_stage_slabs = 0;
   h->eri_ready = true;
   return SCFB_OK;
 }

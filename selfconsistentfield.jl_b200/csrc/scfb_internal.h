@@ -43,8 +43,9 @@ struct scfb_handle_s {
   uint64_t eri_elems = 0;
   bool eri_ready = false;
   bool allow_partial = false;   // n_ranks > 1 without an exchange: return this rank's partial instead of failing
-  bool pk_rows_seen_all = false;  // packed layout: the streamed pack (scfb_eri_pack_slabs) covered every owned i
-  uint64_t* slab_seen = nullptr;  // host bitmap of the owned nu-slabs uploaded so far (full layout)
+  uint64_t* slab_seen = nullptr;  // host bitmap of the owned nu-slabs (packed8: first indices i) uploaded so far
+  double* pack_stage = nullptr;   // packed8: device staging for the nu-slabs being packed
+  size_t pack_stage_slabs = 0;
 
   // device scratch
   double* d_density = nullptr;  // n*n*2   (host-pointer API staging)
@@ -138,7 +139,7 @@ uint64_t scfb_packed_dq_elems(int n);
 int scfb_packed_upload_table(scfb_handle_s* h);
 int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density, const double* d_total);
 int scfb_launch_generate_packed(scfb_handle_s* h, int family, uint64_t seed, const double* d_aux);
-void scfb_pack_host(const double* full, int n, int i_lo, int i_hi, double* out);
+int scfb_launch_pack_slabs(scfb_handle_s* h, const double* d_slabs, int i_first, int count);
 // eri_gen.cu
 int scfb_launch_generate_full(scfb_handle_s* h, int family, uint64_t seed, const double* d_aux);
 // scfb_api.cu

@@ -112,13 +112,14 @@ def load_integral_hdf5(path, slab_batch=None, **builder_kw):
     slab_batch=N streams the tensor to the device N nu-slabs at a time (file row v IS Julia's
     column-major slab eri[:,:,:,v]), reading only the rows this builder's shard owns — the
     whole tensor never exists on the host (the reference's TODO at load_integral_hdf5.jl:9-10);
-    `integrals["electron_repulsion_bbbb"]` is then None."""
+    `integrals["electron_repulsion_bbbb"]` is then None.  With layout="packed8" the slabs are
+    packed on the device as they arrive (csrc/jk_packed.cu: pack_slabs_kernel), so the n^4 tensor
+    never exists on the device either."""
     from .minih5 import MiniH5
     f = MiniH5(path)
     if slab_batch:
         n = f.shape("electron_repulsion_bbbb")[0]
         builder = JKBuilderCUDA(n, **builder_kw)
-        assert builder.layout == "full", "slab streaming targets the full layout"
         lo, hi = builder.shard_range
         for first in range(lo, hi, slab_batch):
             rows = f.read_rows("electron_repulsion_bbbb", first, min(first + slab_batch, hi))
@@ -190,8 +191,9 @@ def compute_pulay_error(fock, density, overlap, *, builder):
 
 
 def compute_roothaan_effective_fock(fock, density, overlap):
-    """compute_fock_matrix.jl:82-123 (ROHF; O(n^3) host algebra — outside the hot-path scope,
-    SURVEY.md §8f rank 4)."""
+    """compute_fock_matrix.jl:82-123 for HOST arrays (the generic mode with several two-electron
+    builders); the device-resident loop builds the same matrix on the GPU (csrc/dense.cu:
+    rohf_effective_fock)."""
     da, db = density[:, :, 0], density[:, :, 1]
     fa, fb = fock[:, :, 0], fock[:, :, 1]
     s = overlap
@@ -548,16 +550,17 @@ class DeviceScf:
         e0 = float(sum(problem.terms_0e.values()))
         self._call("scfb_scf_setup", capi.ptr(s), capi.ptr(hc), C.c_double(e0), problem.n_elec[0],
                    problem.n_elec[1], problem.n_orb, int(problem.restricted), n_diis_size)
-        ns = C.c_int()
+        ns, nd = C.c_int(), C.c_int()
         self._call("scfb_scf_n_spin", C.byref(ns))
-        self.n_spin = ns.value
+        self._call("scfb_scf_n_densities", C.byref(nd))
+        self.n_spin, self.n_dens = ns.value, nd.value     # ROHF: one Fock block, two densities
 
     def _call(self, name, *args):
         capi.check(getattr(capi.lib(), name)(self._h, *args), self._h)
 
     def set_density(self, density):
-        d = capi.as_f64_colmajor(density, (self.n, self.n, self.n_spin))
-        self._call("scfb_scf_set_density", self.n_spin, capi.ptr(d))
+        d = capi.as_f64_colmajor(density, (self.n, self.n, self.n_dens))
+        self._call("scfb_scf_set_density", self.n_dens, capi.ptr(d))
 
     def set_fock(self, fock):
         f = capi.as_f64_colmajor(fock, (self.n, self.n, self.n_spin))
@@ -593,6 +596,8 @@ class DeviceScf:
 
     def get(self, what):
         n, ns = self.n, self.n_spin
+        if what in (self.DENSITY, self.DENSITY_PREV):
+            ns = self.n_dens
         shape = (n, ns) if what in (self.ORBEN, self.ORBEN_PREV) else (n, n, ns)
         out = np.empty(shape, order="F")
         self._call("scfb_scf_get", what, capi.ptr(out))
@@ -605,9 +610,7 @@ def _device_eligible(problem):
     b = next(iter(problem.terms_2e.values()))
     if not isinstance(b, JKBuilderCUDA):
         return None
-    if problem.restricted and problem.n_elec[0] != problem.n_elec[1]:
-        return None          # ROHF effective Fock is host algebra
-    return b
+    return b                 # RHF, UHF and ROHF (Roothaan effective Fock on the device) all qualify
 
 
 # --------------------------------------------------------------------------------------
@@ -620,7 +623,7 @@ def run_scf(problem, guess_density, max_iter=100, ediis_max_error_norm=0.1, mode
     holds the energies of the newest Fock build.  mode: "auto" | "device" | "generic"."""
     builder = _device_eligible(problem) if mode in ("auto", "device") else None
     if mode == "device" and builder is None:
-        raise ValueError("device mode needs exactly one JKBuilderCUDA term and an RHF/UHF problem")
+        raise ValueError("device mode needs exactly one JKBuilderCUDA term")
     if builder is not None:
         return _run_scf_device(problem, builder, guess_density, max_iter, ediis_max_error_norm,
                                verbose, **kwargs)
@@ -673,7 +676,7 @@ def _run_scf_device(problem, builder, guess_density, max_iter, ediis_max_error_n
     n_diis_size = kwargs.get("n_diis_size", 5)
     dev = DeviceScf(problem, builder, n_diis_size)
     n_spin = dev.n_spin
-    assert guess_density.shape == (dev.n, dev.n, n_spin)
+    assert guess_density.shape == (dev.n, dev.n, dev.n_dens)
     damping = EDIIS(problem, **kwargs)
     scfconv, switched, n_iter = None, False, 0
     dev.set_density(guess_density)
