@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """BASELINE.json config 2: synthetic (chain family) RHF, complete SCF loop with EDIIS->cDIIS,
 everything O(n^3)+ on the device.  Prints one JSON line with the per-phase wall time.
-  python benchmarks/scf_loop.py [--n-bas 128] [--layout full|packed8] [--unrestricted]
+  python benchmarks/scf_loop.py [--n-bas 128] [--layout full|packed8] [--unrestricted] [--devices G]
+--devices G shards the ERI over GPUs 0..G-1 behind ONE builder of this one process
+(scfb_create_multi): BASELINE configs 4 / 5 ("chain for one SCF") as a complete
+device-resident SCF — dense algebra on device 0, every GPU streaming its shard each Fock build.
 (The energy is checked against the CPU oracle by tests/test_scf_gpu.py::test_config2_*, not here:
 only tests/, smoke() and bench.py's CPU baseline may touch oracle/.)"""
 import argparse
@@ -22,11 +25,13 @@ def main():
     p.add_argument("--n-bas", type=int, default=128)
     p.add_argument("--layout", default="full")
     p.add_argument("--unrestricted", action="store_true")
+    p.add_argument("--devices", type=int, default=0)
     a = p.parse_args()
     n = a.n_bas
     model = scf_b200.synthetic.ChainModel(n)
     t0 = time.perf_counter()
-    builder = scf_b200.JKBuilderCUDA.synthetic(n, "chain", 0, aux=model.aux, layout=a.layout)
+    kw_dev = {"devices": list(range(a.devices))} if a.devices > 1 else {}
+    builder = scf_b200.JKBuilderCUDA.synthetic(n, "chain", 0, aux=model.aux, layout=a.layout, **kw_dev)
     builder.sync()
     t_gen = time.perf_counter() - t0
     problem = scf_b200.ScfProblem(model.overlap, model.n_elec(a.unrestricted), n, not a.unrestricted,
@@ -52,7 +57,9 @@ def main():
     t0 = time.perf_counter()
     res = scf_b200.run_scf(problem, guess, verbose=False, **kw)
     t_scf = time.perf_counter() - t0
-    line = {"config": f"chain {'UHF' if a.unrestricted else 'RHF'} n_bf={n} {a.layout}, device-resident SCF",
+    line = {"config": f"chain {'UHF' if a.unrestricted else 'RHF'} n_bf={n} {a.layout}, device-resident SCF"
+                      + (f", one handle over {a.devices} GPUs" if a.devices > 1 else ""),
+            "energy_per_site": res["energies_newest"]["total"] / n,
             "converged": bool(res["converged"]), "n_iter": res["n_iter"],
             "e_total": res["energies_newest"]["total"], "scf_seconds": t_scf,
             "ms_per_iteration": 1e3 * t_scf / res["n_iter"],

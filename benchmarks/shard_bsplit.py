@@ -17,7 +17,8 @@ def one(a):
     import scf_b200
     from scf_b200 import synthetic
     n, n_spin = a.n_bas, a.n_spin
-    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synthetic.SEED_ERI, rank=a.rank, n_ranks=a.ranks, allow_partial=True)
+    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synthetic.SEED_ERI, layout=a.layout, rank=a.rank, n_ranks=a.ranks,
+                                         allow_partial=True)
     dev = torch.device("cuda:0")
     d = torch.from_numpy(np.stack([synthetic.hash_density(n, synthetic.SEED_DA + s)
                                    for s in range(n_spin)], axis=0)).to(dev).contiguous()
@@ -46,6 +47,7 @@ if __name__ == "__main__":
     ap.add_argument("--ranks", type=int, default=8)
     ap.add_argument("--rank", type=int, default=5)
     ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--layout", default="full")
     ap.add_argument("--sweep", default="auto,1,2,4,8")
     ap.add_argument("--child", action="store_true")
     a = ap.parse_args()
@@ -59,4 +61,4 @@ if __name__ == "__main__":
                 env["SCFB_FULL_BSPLIT"] = v
             subprocess.run([sys.executable, __file__, "--child", "--n-bas", str(a.n_bas), "--n-spin",
                             str(a.n_spin), "--ranks", str(a.ranks), "--rank", str(a.rank), "--steps",
-                            str(a.steps)], env=env, check=True)
+                            str(a.steps), "--layout", a.layout], env=env, check=True)

@@ -164,7 +164,7 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
                                             double* __restrict__ Kp, double* __restrict__ Jp,
                                             double* __restrict__ sm,  // this warp's PkSmem block
                                             int n, int iA, bool has_b, int k0, int l0, int lane,
-                                            uint32_t rot) {
+                                            uint32_t rot, int j_lo, int j_cnt) {
   using S = PkSmem<NSPIN, KC, DEPTH>;
   constexpr int NK = S::NK, NV = S::NV, DKN = S::DKN;
   const int iB = iA + 1;
@@ -227,11 +227,12 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
 #pragma unroll
   for (int s = 0; s < NSPIN; ++s) a2A[s][0] = a2A[s][1] = a2B[s][0] = a2B[s][1] = 0.0;
 
-  const int rows = iT + 1;  // stream A has no row j = iB
+  // The item covers the rows j in [j_lo, j_hi) of both streams (stream A has no row j = iB).
   // Rows are visited in a rotated order that differs per (i, k-chunk), so that concurrently
   // running warps do not all RED into the same K'[j,:] row at the same time; the l-blocks of one
-  // (i, k-chunk) share the order (their reads of a row are neighbours in memory).
-  const int j_first = (int)(rot % (uint32_t)rows);
+  // (i, k-chunk, row range) share the order (their reads of a row are neighbours in memory).
+  const int rows = j_cnt, j_hi = j_lo + j_cnt;
+  const int j_first = j_lo + (int)(rot % (uint32_t)rows);
 
   // ---- load side: row pair jl goes to the ring DEPTH-1 pairs ahead of its use (warp-uniform state) ----
   int jl = j_first;
@@ -282,10 +283,10 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
     }
     if (lane < NK + 2) cp_async8(ring_dk_a + stage * DKN * 8, dk_base + (size_t)jl * dk_step);
     // advance to the next row in the rotated order
-    if (jl + 1 == rows) {
-      jl = 0;
-      rowA = reinterpret_cast<const char*>(eri_a);
-      rowB = reinterpret_cast<const char*>(eri_b);
+    if (jl + 1 == j_hi) {
+      jl = j_lo;
+      rowA = reinterpret_cast<const char*>(eri_a + (uint64_t)j_lo * EA + seg_off(j_lo));
+      rowB = reinterpret_cast<const char*>(eri_b + (uint64_t)j_lo * EB + seg_off(j_lo));
     } else {
       const uint32_t c2 = (uint32_t)seg_len(jl + 1) * 8u;
       rowA += stepA + c2;
@@ -314,7 +315,7 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
       }
       const double tot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
       int jr = j_tile + red_r;
-      if (jr >= rows) jr -= rows;
+      if (jr >= j_hi) jr -= rows;
       if (red_v == NK) {
         if (jr <= iA) atomicAdd(Jp + EA + jr, tot);  // J~[pr(iA,j)]
       } else if (red_v == NK + 1) {
@@ -395,7 +396,7 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
       if (l0_in) atomicAdd(kj + s * dstride, z[s][0]);
       if (l1_in) atomicAdd(kj + s * dstride + 1, z[s][1]);
     }
-    jc = jc + 1 == rows ? 0 : jc + 1;
+    jc = jc + 1 == j_hi ? j_lo : jc + 1;
   };
 
   auto commit = [] { asm volatile("cp.async.commit_group;" ::: "memory"); };
@@ -474,14 +475,16 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
 // pair first and the l-blocks of one (pair, k-chunk) adjacent.  (One-warp CTAs launched per triple
 // left 20-35 % of the warp slots empty: dead triples beyond the triangle, block-launch latency and
 // warps that could not be placed on a sub-partition with enough free registers.)
-// item = pair << 16 | k-chunk << 6 | l-block; pair z covers iA = i_hi - 2 - 2z, iB = iA + 1; the
-// last pair of an odd-sized shard is the single index i_lo (stream A only).
+// item = (pair << 16 | k-chunk << 6 | l-block, j_lo << 16 | row count); pair z covers iA = i_hi - 2 - 2z,
+// iB = iA + 1; the last pair of an odd-sized shard is the single index i_lo (stream A only).  The
+// rows of a (pair, k-chunk, l-block) are cut into ranges so that every warp slot sees a few dozen
+// items (one item over all <= n rows takes up to ~0.8 ms: too coarse for a 1/8 shard).
 template <int NSPIN, int KC, int DEPTH, int WARPS, bool VECD>
 __global__ void __launch_bounds__(32 * WARPS, 1)
 jk_packed_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Btab,
                  uint64_t shard_offset, const double* __restrict__ D, size_t dstride,
                  const double* __restrict__ dq2, double* __restrict__ Kp, double* __restrict__ Jp,
-                 int n, int i_lo, int i_hi, const uint32_t* __restrict__ items, int n_items,
+                 int n, int i_lo, int i_hi, const uint2* __restrict__ items, int n_items,
                  int* __restrict__ sched) {
   extern __shared__ __align__(16) double pk_smem[];
   const int lane = threadIdx.x & 31;
@@ -490,7 +493,9 @@ jk_packed_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Bt
     int idx = lane == 0 ? atomicAdd(sched, 1) : 0;
     idx = __shfl_sync(0xffffffffu, idx, 0);
     if (idx >= n_items) break;
-    const uint32_t it = __ldg(items + idx);
+    const uint2 it2 = __ldg(items + idx);
+    const uint32_t it = it2.x;
+    const int j_lo = (int)(it2.y >> 16), j_cnt = (int)(it2.y & 0xffffu);
     int iA = i_hi - 2 - 2 * (int)(it >> 16);
     const bool has_b = iA >= i_lo;
     if (!has_b) iA = i_lo;
@@ -503,11 +508,11 @@ jk_packed_kernel(const double* __restrict__ eri, const uint64_t* __restrict__ Bt
     const double* eri_b = eri + (Btab[iT] - shard_offset);
     const uint32_t rot = (uint32_t)kc * 40503u + (uint32_t)iA * 17u;
     if (k0 + KC - 1 >= iA)
-      packed_item<NSPIN, KC, DEPTH, 2, VECD>(eri_a, eri_b, D, dstride, dq2, Kp, Jp, sm, n, iA, has_b, k0, l0, lane, rot);
+      packed_item<NSPIN, KC, DEPTH, 2, VECD>(eri_a, eri_b, D, dstride, dq2, Kp, Jp, sm, n, iA, has_b, k0, l0, lane, rot, j_lo, j_cnt);
     else if (wl + 63 <= k0)
-      packed_item<NSPIN, KC, DEPTH, 0, VECD>(eri_a, eri_b, D, dstride, dq2, Kp, Jp, sm, n, iA, has_b, k0, l0, lane, rot);
+      packed_item<NSPIN, KC, DEPTH, 0, VECD>(eri_a, eri_b, D, dstride, dq2, Kp, Jp, sm, n, iA, has_b, k0, l0, lane, rot, j_lo, j_cnt);
     else
-      packed_item<NSPIN, KC, DEPTH, 1, VECD>(eri_a, eri_b, D, dstride, dq2, Kp, Jp, sm, n, iA, has_b, k0, l0, lane, rot);
+      packed_item<NSPIN, KC, DEPTH, 1, VECD>(eri_a, eri_b, D, dstride, dq2, Kp, Jp, sm, n, iA, has_b, k0, l0, lane, rot, j_lo, j_cnt);
     __syncwarp();
   }
 }
@@ -648,18 +653,26 @@ uint64_t scfb_packed_offset(int i) {  // B[i]: padded elements of all rows with 
 
 uint64_t scfb_packed_dq_elems(int n) { return seg_off(n); }
 
-// i-blocks owned by `rank`: contiguous ranges balanced by stored-element count (~ i^4 / 8).
+// i-blocks owned by `rank`: contiguous ranges balanced by WORK, not bytes.  A warp spends about the
+// same time on a row of its (k-chunk, l-block) tile whether its 64 l-lanes are all inside the
+// triangle or not, so the cost of first index i is its number of (tile, row) steps,
+// (i+1) * sum over k-chunks of the l-blocks they touch; balancing stored elements instead made the
+// small-i shard 40 % slower than the large-i one (0.72 vs 0.51 ms at n_bf = 384 over 8 ranks).
 void scfb_packed_split(int n, int rank, int n_ranks, int* i_lo, int* i_hi) {
-  std::vector<uint64_t> B(n + 1, 0);
-  for (int i = 0; i < n; ++i) B[i + 1] = B[i] + (uint64_t)(i + 1) * seg_off(i) + seg_off(i + 1);
+  std::vector<long double> W(n + 1, 0.0L);
+  for (int i = 0; i < n; ++i) {
+    long double tiles = 0;
+    for (int kc = 0; kc <= i / 8; ++kc) tiles += std::min(8 * kc + 7, i) / 64 + 1;
+    W[i + 1] = W[i] + tiles * (i + 1);
+  }
   auto bound = [&](int g) -> int {
     if (g <= 0) return 0;
     if (g >= n_ranks) return n;
-    const long double target = (long double)B[n] * g / n_ranks;
+    const long double target = W[n] * g / n_ranks;
     int lo = 0, hi = n;
-    while (lo < hi) {  // smallest i with B[i] >= target
+    while (lo < hi) {  // smallest i with W[i] >= target
       const int mid = (lo + hi) / 2;
-      if ((long double)B[mid] >= target) hi = mid; else lo = mid + 1;
+      if (W[mid] >= target) hi = mid; else lo = mid + 1;
     }
     return lo;
   };
@@ -679,25 +692,46 @@ int scfb_packed_upload_table(scfb_handle_s* h) {
   return SCFB_OK;
 }
 
-// Live work items of this shard for k-chunk width kc_w, in the order the warps draw them.
-static int build_items(scfb_handle_s* h, int kc_w, int slot) {
-  std::vector<uint32_t> items;
+// Live work items of this shard for k-chunk width kc_w, in the order the warps draw them: heaviest
+// pair first, the l-blocks of one (pair, k-chunk, row range) adjacent.  Row ranges are sized so that
+// every warp slot of the device draws >= ~16 items (a dynamic schedule's tail is one item long).
+static int build_items(scfb_handle_s* h, int kc_w, int warps_per_sm, int slot) {
+  std::vector<uint2> items;
   const int n_pairs = (h->i_hi - h->i_lo + 1) / 2;
+  uint64_t warp_rows = 0;  // total (warp, row pair) steps of the shard
   for (int z = 0; z < n_pairs; ++z) {
     int iA = h->i_hi - 2 - 2 * z;
     const bool has_b = iA >= h->i_lo;
     if (!has_b) iA = h->i_lo;
     const int iT = has_b ? iA + 1 : iA;
-    for (int kc = iT / kc_w; kc >= 0; --kc) {  // longest segments first
-      const int kmax = std::min(kc * kc_w + kc_w - 1, iT);
-      for (int lb = 0; 64 * lb <= kmax; ++lb) items.push_back((uint32_t)z << 16 | (uint32_t)kc << 6 | (uint32_t)lb);
+    for (int kc = iT / kc_w; kc >= 0; --kc) warp_rows += (uint64_t)(std::min(kc * kc_w + kc_w - 1, iT) / 64 + 1) * (iT + 1);
+  }
+  const uint64_t slots = (uint64_t)(h->n_sm > 0 ? h->n_sm : 148) * warps_per_sm;
+  // (an item costs ~5 us of prologue / ring fill / epilogue next to ~1.5 us per row pair: ranges
+  // shorter than 64 rows were measured to cost a small shard 40 %)
+  int j_max = (int)(warp_rows / (16 * slots));
+  j_max = std::max(64, std::min(j_max, 4096));
+  for (int z = 0; z < n_pairs; ++z) {
+    int iA = h->i_hi - 2 - 2 * z;
+    const bool has_b = iA >= h->i_lo;
+    if (!has_b) iA = h->i_lo;
+    const int iT = has_b ? iA + 1 : iA;
+    const int rows = iT + 1, n_ranges = (rows + j_max - 1) / j_max;
+    for (int r = 0; r < n_ranges; ++r) {
+      const int j_lo = (int)((int64_t)rows * r / n_ranges), j_hi = (int)((int64_t)rows * (r + 1) / n_ranges);
+      for (int kc = iT / kc_w; kc >= 0; --kc) {  // longest segments first
+        const int kmax = std::min(kc * kc_w + kc_w - 1, iT);
+        for (int lb = 0; 64 * lb <= kmax; ++lb)
+          items.push_back(make_uint2((uint32_t)z << 16 | (uint32_t)kc << 6 | (uint32_t)lb,
+                                     (uint32_t)j_lo << 16 | (uint32_t)(j_hi - j_lo)));
+      }
     }
   }
   h->pk_n_items[slot] = (int)items.size();
   if (items.empty()) return SCFB_OK;
-  cudaError_t e = cudaMalloc(&h->pk_items[slot], items.size() * sizeof(uint32_t));
+  cudaError_t e = cudaMalloc(&h->pk_items[slot], items.size() * sizeof(uint2));
   if (e == cudaSuccess)
-    e = cudaMemcpy(h->pk_items[slot], items.data(), items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    e = cudaMemcpy(h->pk_items[slot], items.data(), items.size() * sizeof(uint2), cudaMemcpyHostToDevice);
   if (e != cudaSuccess)
     return scfb_fail(h, e == cudaErrorMemoryAllocation ? SCFB_ERR_OOM : SCFB_ERR_CUDA, "packed item list: %s",
                      cudaGetErrorString(e));
@@ -710,8 +744,12 @@ template <int NSPIN, int KC, int DEPTH, int WARPS, bool VECD>
 static int launch_packed_cfg(scfb_handle_s* h, double* Jp, double* Kp, size_t dstride, int slot) {
   const size_t smem = (size_t)WARPS * PkSmem<NSPIN, KC, DEPTH>::TOTAL * sizeof(double);
   auto kern = jk_packed_kernel<NSPIN, KC, DEPTH, WARPS, VECD>;
+  if (h->n_sm == 0) {
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
+    if (h->n_sm <= 0) h->n_sm = 148;
+  }
   if (!h->pk_items[slot] && h->pk_n_items[slot] < 0) {  // first launch of this instantiation on this handle
-    if (int rc = build_items(h, KC, slot)) return rc;
+    if (int rc = build_items(h, KC, WARPS, slot)) return rc;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "jk_packed_kernel attributes: %s", cudaGetErrorString(e));
   }

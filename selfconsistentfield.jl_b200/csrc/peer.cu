@@ -73,8 +73,8 @@ __device__ __forceinline__ bool gate_wait(const unsigned long long* flags, int n
           const volatile unsigned long long* f = flags + (size_t)r * kFlagStride;
           unsigned long long w = 0;
           while (*f < epoch) {
-            __nanosleep(1000);
-            if (++w > spin_limit) {
+            __nanosleep(250);
+            if (++w > 4 * spin_limit) {
               good = 0;
               break;
             }
@@ -86,8 +86,8 @@ __device__ __forceinline__ bool gate_wait(const unsigned long long* flags, int n
         __threadfence();
         res = good;
       } else {
-        __nanosleep(500);
-        if (++spins > 4 * spin_limit * (unsigned long long)n_ranks) res = 0;  // the waiter itself never answered
+        __nanosleep(100);
+        if (++spins > 20 * spin_limit * (unsigned long long)n_ranks) res = 0;  // the waiter itself never answered
       }
     }
     ok = res;

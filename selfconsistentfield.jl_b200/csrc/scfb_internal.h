@@ -60,7 +60,7 @@ struct scfb_handle_s {
   unsigned int* grid_done = nullptr;  // CTAs of the running K1 launch that have finished
   int n_sm = 0;                 // SM count of this handle's device (lazily queried)
   bool tma_attr[3] = {false, false, false};  // per NSPIN: smem attributes of jk_full_tma_kernel set on this device
-  uint32_t* pk_items[2] = {};   // live work items of jk_packed_kernel per spin count (built at first launch)
+  uint2* pk_items[2] = {};   // live work items of jk_packed_kernel per spin count (built at first launch)
   int pk_n_items[2] = {-1, -1};
   int b_splits = 1;             // CTAs sharing one (nu, c-chunk) work item along b
   uint64_t kpart_elems = 0;

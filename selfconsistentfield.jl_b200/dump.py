@@ -64,11 +64,18 @@ def dump_molsturm_hdf5(integrals, scfres, file, export_eri_bbbb=False, export_er
     if export_eri_ffff:
         raise NotImplementedError("Exporting eri in orbitals not yet implemented.")
     problem, energies, change = scfres["problem"], scfres["energies"], scfres["energy_change"]
+    if scfres.get("orbcoeff") is None or scfres.get("orben") is None:
+        # run_scf.jl:40 breaks before :48: a run that converges in its very first iteration returns
+        # the guess iterate, which has no orbitals yet (the reference would fail inside concat_spin)
+        raise ValueError("scfres holds no orbitals (SCF converged before the first Roothaan step was "
+                         "accepted): nothing to dump; rerun with tighter thresholds or another guess")
     fock, orbcoeff = np.asarray(scfres["fock"]), np.asarray(scfres["orbcoeff"])
     n_bas = fock.shape[0]
     julia = {                                   # name -> array with Julia index semantics
         "n_alpha": np.int64(problem.n_elec[0]), "n_beta": np.int64(problem.n_elec[1]),
-        "n_bas": np.int64(n_bas), "restricted": np.uint8(bool(problem.restricted)),
+        "n_bas": np.int64(n_bas), "restricted": np.uint8(bool(problem.restricted)),   # plain 0/1 byte; the reference's
+        # sanitise step re-creates it as h5py's bool enum over int8 (same storage size and values, a
+        # different HDF5 datatype class) — readers that test the value are unaffected
         "overlap_bb": build_ab_matrix(problem.overlap),
         "n_orbs_alpha": np.int64(problem.n_orb), "n_orbs_beta": np.int64(problem.n_orb),
         "orben_f": concat_spin(scfres["orben"]),

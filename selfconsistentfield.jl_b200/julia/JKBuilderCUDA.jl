@@ -256,8 +256,12 @@ function run_scf_device(problem::ScfProblem, guess_density::AbstractArray;
                         conditioning_threshold=1e-14, coefficient_threshold=1e-6, kwargs...)
     @assert length(problem.terms_2e) == 1
     b = first(values(problem.terms_2e))::JKBuilderCUDA
-    n_spin = size(guess_density, 3)
     scf_device_setup!(b, problem; n_diis_size=n_diis_size)
+    # spin blocks of the Fock iterate: 1 for RHF and ROHF (two densities, one effective Fock block,
+    # compute_fock_matrix.jl:61-65), 2 for UHF — what spinloop(iterstate.fock) runs over (diis.jl:8)
+    ns = Ref{Cint}(0)
+    check(ccall((:scfb_scf_n_spin, libscf), Cint, (Ptr{Cvoid}, Ref{Cint}), b.handle, ns), b.handle)
+    n_spin = Int(ns[])
     scf_device_set_density!(b, guess_density)
     energies, _ = scf_device_fock!(b)                       # run_scf.jl:16
     use_ediis = true                                        # run_scf.jl:8
