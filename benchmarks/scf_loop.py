@@ -40,7 +40,7 @@ def main():
                                   {"coulomb+exchange": builder})
     guess = scf_b200.compute_guess(problem)
     # instrument the device step
-    phases = {"fock": 0.0, "roothaan": 0.0, "diis_push": 0.0, "diis_extrapolate": 0.0}
+    phases = {"__init__": 0.0, "fock": 0.0, "roothaan": 0.0, "diis_push": 0.0, "diis_extrapolate": 0.0, "get": 0.0}
     for name in list(phases):
         orig = getattr(S.DeviceScf, name)
 
@@ -63,7 +63,9 @@ def main():
             "converged": bool(res["converged"]), "n_iter": res["n_iter"],
             "e_total": res["energies_newest"]["total"], "scf_seconds": t_scf,
             "ms_per_iteration": 1e3 * t_scf / res["n_iter"],
-            "phase_ms_per_iteration": {k: 1e3 * v / res["n_iter"] for k, v in phases.items()},
+            "phase_ms_per_iteration": {k: 1e3 * v / res["n_iter"] for k, v in phases.items()
+                                       if k not in ("__init__", "get")},
+            "setup_ms": 1e3 * phases["__init__"], "result_download_ms": 1e3 * phases["get"],
             "eri_generate_seconds": t_gen, "fock_kernel_ms": builder.last_build_ms()[0]}
     print(json.dumps(line))
 

@@ -390,9 +390,27 @@ int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core,
   SCFB_REQUIRE(h, n_diis_size >= 1 && n_diis_size <= kMaxPairs, "n_diis_size must be in [1, %d]",
                kMaxPairs);
   SCFB_CUDA(h, cudaSetDevice(h->device));
-  scfb_scf_free(h);
-  scfb_scf_state* st = new scfb_scf_state();
-  h->scf = st;
+  // A second SCF on the same handle (same sizes, e.g. RHF after the guess or a restart) reuses the
+  // resident buffers, cuSOLVER workspaces and the overlap's Cholesky workspace: ~40 cudaMalloc /
+  // cudaFree calls (each a device synchronisation) would otherwise cost more than a small SCF itself.
+  const bool want_rohf = restricted && n_elec_a != n_elec_b;
+  int want_eig;
+  {
+    const char* eig = std::getenv("SCFB_EIG");
+    // default (same-box timings in profiles/README.md): the warm-started Jacobi wins while the matrices are
+    // small (n_bf = 128: 2.9 vs 3.6 ms per RHF iteration, 3.1 vs 5.6 UHF), Dsyevd on the cached factor beyond
+    want_eig = !eig ? (n < 200 ? 2 : 1)
+                    : (std::strcmp(eig, "syevd") == 0 ? 1 : (std::strcmp(eig, "warm") == 0 ? 2 : 0));
+  }
+  const bool want_jacobi = [] { const char* e = std::getenv("SCFB_EIG"); return e && std::strcmp(e, "jacobi") == 0; }();
+  scfb_scf_state* st = h->scf;
+  const bool reuse = st && st->n == n && st->cap == n_diis_size && st->eig_mode == want_eig &&
+                     (st->R != nullptr || !want_rohf) && ((st->jacobi != nullptr) == want_jacobi);
+  if (!reuse) {
+    scfb_scf_free(h);
+    st = new scfb_scf_state();
+    h->scf = st;
+  }
   st->n = n;
   st->n_orb = n_orb;
   st->n_elec[0] = n_elec_a;
@@ -409,72 +427,72 @@ int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core,
   st->solver = static_cast<cusolverDnHandle_t>(h->solver);
   cublasSetStream(st->blas, h->stream);
   cusolverDnSetStream(st->solver, h->stream);
-  auto alloc = [&](double** p, size_t count) { return cudaMalloc(p, count * sizeof(double)); };
-  SCFB_CUDA(h, alloc(&st->S, n2));
-  SCFB_CUDA(h, alloc(&st->H, n2));
-  SCFB_CUDA(h, alloc(&st->F, 2 * n2));
-  SCFB_CUDA(h, alloc(&st->Fnew, 2 * n2));
-  SCFB_CUDA(h, alloc(&st->D, 2 * n2));
-  SCFB_CUDA(h, alloc(&st->Dtot, n2));
-  SCFB_CUDA(h, alloc(&st->G, 2 * n2));
-  SCFB_CUDA(h, alloc(&st->E, 2 * n2));
-  SCFB_CUDA(h, alloc(&st->C, 2 * n2));
-  SCFB_CUDA(h, alloc(&st->eps, 2 * (size_t)n));
-  SCFB_CUDA(h, alloc(&st->Cprev, 2 * n2));
-  SCFB_CUDA(h, alloc(&st->epsprev, 2 * (size_t)n));
-  SCFB_CUDA(h, alloc(&st->Dprev, 2 * n2));
-  SCFB_CUDA(h, alloc(&st->T1, n2));
-  SCFB_CUDA(h, alloc(&st->T2, n2));
-  SCFB_CUDA(h, alloc(&st->Bw, n2));
-  SCFB_CUDA(h, alloc(&st->scal, kScal));
-  SCFB_CUDA(h, alloc(&st->coef, kMaxPairs));
-  SCFB_CUDA(h, alloc(&st->Fh, 2 * (size_t)st->cap * n2));
-  SCFB_CUDA(h, alloc(&st->Eh, 2 * (size_t)st->cap * n2));
-  SCFB_CUDA(h, alloc(&st->Dh, 2 * (size_t)st->cap * n2));
-  SCFB_CUDA(h, cudaMalloc(&st->dev_info, sizeof(int)));
-  SCFB_CUDA(h, cudaMallocHost(&st->h_scal, kScal * sizeof(double)));
-  SCFB_SOLVER(h, cusolverDnDsygvd_bufferSize(st->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
-                                             CUBLAS_FILL_MODE_LOWER, n, st->T1, n, st->Bw, n, st->eps,
-                                             &st->lwork));
-  SCFB_CUDA(h, alloc(&st->work, st->lwork > 0 ? st->lwork : 1));
-  if (st->rohf) SCFB_CUDA(h, alloc(&st->R, 6 * n2));
-  // eigensolver: SCFB_EIG = sygvd | syevd | warm | jacobi (see solve_orbitals)
-  {
-    const char* eig = std::getenv("SCFB_EIG");
-    // default (same-box timings in profiles/README.md): the warm-started Jacobi wins while the matrices are
-    // small (n_bf = 128: 2.9 vs 3.6 ms per RHF iteration, 3.1 vs 5.6 UHF), Dsyevd on the cached factor beyond
-    st->eig_mode = !eig ? (n < 200 ? 2 : 1)
-                        : (std::strcmp(eig, "syevd") == 0 ? 1 : (std::strcmp(eig, "warm") == 0 ? 2 : 0));
-  }
-  if (st->eig_mode != 0) {
-    SCFB_CUDA(h, alloc(&st->Lchol, n2));
-    if (st->eig_mode == 1) {
-      SCFB_SOLVER(h, cusolverDnDsyevd_bufferSize(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
-                                                 st->T1, n, st->eps, &st->lwork_ev));
-    } else {
-      SCFB_CUDA(h, alloc(&st->Yprev, 2 * n2));
-      SCFB_SOLVER(h, cusolverDnCreateSyevjInfo(&st->jw));
-      SCFB_SOLVER(h, cusolverDnXsyevjSetTolerance(st->jw, 1e-15));
-      SCFB_SOLVER(h, cusolverDnXsyevjSetMaxSweeps(st->jw, 100));
-      SCFB_SOLVER(h, cusolverDnXsyevjSetSortEig(st->jw, 1));
-      SCFB_SOLVER(h, cusolverDnDsyevj_bufferSize(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
-                                                 st->T1, n, st->eps, &st->lwork_ev, st->jw));
+  if (!reuse) {
+    auto alloc = [&](double** p, size_t count) { return cudaMalloc(p, count * sizeof(double)); };
+    SCFB_CUDA(h, alloc(&st->S, n2));
+    SCFB_CUDA(h, alloc(&st->H, n2));
+    SCFB_CUDA(h, alloc(&st->F, 2 * n2));
+    SCFB_CUDA(h, alloc(&st->Fnew, 2 * n2));
+    SCFB_CUDA(h, alloc(&st->D, 2 * n2));
+    SCFB_CUDA(h, alloc(&st->Dtot, n2));
+    SCFB_CUDA(h, alloc(&st->G, 2 * n2));
+    SCFB_CUDA(h, alloc(&st->E, 2 * n2));
+    SCFB_CUDA(h, alloc(&st->C, 2 * n2));
+    SCFB_CUDA(h, alloc(&st->eps, 2 * (size_t)n));
+    SCFB_CUDA(h, alloc(&st->Cprev, 2 * n2));
+    SCFB_CUDA(h, alloc(&st->epsprev, 2 * (size_t)n));
+    SCFB_CUDA(h, alloc(&st->Dprev, 2 * n2));
+    SCFB_CUDA(h, alloc(&st->T1, n2));
+    SCFB_CUDA(h, alloc(&st->T2, n2));
+    SCFB_CUDA(h, alloc(&st->Bw, n2));
+    SCFB_CUDA(h, alloc(&st->scal, kScal));
+    SCFB_CUDA(h, alloc(&st->coef, kMaxPairs));
+    SCFB_CUDA(h, alloc(&st->Fh, 2 * (size_t)st->cap * n2));
+    SCFB_CUDA(h, alloc(&st->Eh, 2 * (size_t)st->cap * n2));
+    SCFB_CUDA(h, alloc(&st->Dh, 2 * (size_t)st->cap * n2));
+    SCFB_CUDA(h, cudaMalloc(&st->dev_info, sizeof(int)));
+    SCFB_CUDA(h, cudaMallocHost(&st->h_scal, kScal * sizeof(double)));
+    SCFB_SOLVER(h, cusolverDnDsygvd_bufferSize(st->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
+                                               CUBLAS_FILL_MODE_LOWER, n, st->T1, n, st->Bw, n, st->eps,
+                                               &st->lwork));
+    SCFB_CUDA(h, alloc(&st->work, st->lwork > 0 ? st->lwork : 1));
+    if (want_rohf) SCFB_CUDA(h, alloc(&st->R, 6 * n2));
+    st->eig_mode = want_eig;  // SCFB_EIG = sygvd | syevd | warm | jacobi (see solve_orbitals)
+    if (st->eig_mode != 0) {
+      SCFB_CUDA(h, alloc(&st->Lchol, n2));
+      if (st->eig_mode == 1) {
+        SCFB_SOLVER(h, cusolverDnDsyevd_bufferSize(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
+                                                   st->T1, n, st->eps, &st->lwork_ev));
+      } else {
+        SCFB_CUDA(h, alloc(&st->Yprev, 2 * n2));
+        SCFB_SOLVER(h, cusolverDnCreateSyevjInfo(&st->jw));
+        SCFB_SOLVER(h, cusolverDnXsyevjSetTolerance(st->jw, 1e-15));
+        SCFB_SOLVER(h, cusolverDnXsyevjSetMaxSweeps(st->jw, 100));
+        SCFB_SOLVER(h, cusolverDnXsyevjSetSortEig(st->jw, 1));
+        SCFB_SOLVER(h, cusolverDnDsyevj_bufferSize(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
+                                                   st->T1, n, st->eps, &st->lwork_ev, st->jw));
+      }
+      SCFB_CUDA(h, alloc(&st->work_ev, st->lwork_ev > 0 ? st->lwork_ev : 1));
     }
-    SCFB_CUDA(h, alloc(&st->work_ev, st->lwork_ev > 0 ? st->lwork_ev : 1));
   }
+  st->order[0].clear();
+  st->order[1].clear();
+  st->have_density = st->have_fock = false;
+  st->have_y[0] = st->have_y[1] = false;
+  st->warm_steps[0] = st->warm_steps[1] = 0;
   SCFB_CUDA(h, cudaMemcpyAsync(st->S, overlap, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   SCFB_CUDA(h, cudaMemcpyAsync(st->H, h_core, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   if (st->eig_mode != 0) {  // S = L L' once: the overlap is constant over the SCF (ScfProblem.jl:48-49)
     SCFB_CUDA(h, cudaMemcpyAsync(st->Lchol, st->S, n2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     int lw = 0;
     SCFB_SOLVER(h, cusolverDnDpotrf_bufferSize(st->solver, CUBLAS_FILL_MODE_LOWER, n, st->Lchol, n, &lw));
-    double* w = nullptr;
-    SCFB_CUDA(h, cudaMalloc(&w, (lw > 0 ? lw : 1) * sizeof(double)));
+    double* w = st->T2;  // scratch: n^2 doubles cover potrf's workspace at every size seen; else allocate
+    if ((size_t)lw > n2) SCFB_CUDA(h, cudaMalloc(&w, (size_t)lw * sizeof(double)));
     cusolverStatus_t cs = cusolverDnDpotrf(st->solver, CUBLAS_FILL_MODE_LOWER, n, st->Lchol, n, w, lw, st->dev_info);
     int info = 0;
     cudaMemcpyAsync(&info, st->dev_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
     cudaError_t ce = cudaStreamSynchronize(h->stream);
-    cudaFree(w);
+    if (w != st->T2) cudaFree(w);
     if (cs != CUSOLVER_STATUS_SUCCESS || ce != cudaSuccess || info != 0)
       return scfb_fail(h, SCFB_ERR_CUSOLVER, "Cholesky factorisation of the overlap failed (info=%d): S must be "
                        "symmetric positive definite", info);
