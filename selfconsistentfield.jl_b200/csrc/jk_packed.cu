@@ -123,19 +123,13 @@ template <int NSPIN, int KC, int DEPTH>
 struct PkSmem {
   static constexpr int NK = NSPIN * KC;
   static constexpr int NV = NK + 2;  // lane-reduced values per row pair: K'[j,k] per spin and k, J~[(iA,j)], J~[(iB,j)]
-  // row pairs parked in the row-sum tile between flushes: one flush pass = one lane per (row, value)
-  static constexpr int FR = DEPTH * NV <= 32 ? DEPTH : 1;
-  static_assert(FR * NV <= 32 && DEPTH % FR == 0, "flush geometry");
-  // UHF at KC = 8: the warp-uniform item constants D[iA, k-chunk], D[iB, k-chunk] live in shared memory
-  // (broadcast reads) instead of 64 registers, which is what lets the 2x K state fit 255 registers
-  static constexpr bool DIKS = NK > 8;
+  static_assert(DEPTH * NV <= 32, "one flush pass: one lane per (row, value)");
   static constexpr int DKN = (NK + 3) & ~1;  // D[j, k-chunk] per spin + 2Dtot[(iA,j)] + 2Dtot[(iB,j)], padded even
-  static constexpr int TILE = 0;                                // [FR][NV][YS]
-  static constexpr int RING = TILE + FR * NV * YS;              // [DEPTH][2][KC][32] double2
+  static constexpr int TILE = 0;                                // [DEPTH][NV][YS]
+  static constexpr int RING = TILE + DEPTH * NV * YS;           // [DEPTH][2][KC][32] double2
   static constexpr int RING_DL = RING + DEPTH * 2 * KC * 64;    // [DEPTH][NSPIN][32] double2
   static constexpr int RING_DK = RING_DL + DEPTH * NSPIN * 64;  // [DEPTH][DKN]
-  static constexpr int DIK = RING_DK + DEPTH * DKN + (DEPTH * DKN & 1);  // [2 streams][NSPIN][KC] (DIKS only)
-  static constexpr int TOTAL = DIK + (DIKS ? 2 * NK : 0);
+  static constexpr int TOTAL = RING_DK + DEPTH * DKN;
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t nbytes) {
@@ -172,8 +166,7 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
                                             int n, int iA, bool has_b, int k0, int l0, int lane,
                                             uint32_t rot, int j_lo, int j_cnt) {
   using S = PkSmem<NSPIN, KC, DEPTH>;
-  constexpr int NK = S::NK, NV = S::NV, DKN = S::DKN, FR = S::FR;
-  constexpr bool DIKS = S::DIKS;
+  constexpr int NK = S::NK, NV = S::NV, DKN = S::DKN;
   const int iB = iA + 1;
   const int iT = has_b ? iB : iA;  // largest first index of the item
   const int kmax = min(k0 + KC - 1, iT);
@@ -193,8 +186,7 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
   double* ys = sm + S::TILE;
 
   // per-item constants
-  double dA_l[NSPIN][2], dB_l[NSPIN][2], dA_k[NSPIN][DIKS ? 1 : KC], dB_k[NSPIN][DIKS ? 1 : KC], dq[KC][2];
-  double* dik = sm + S::DIK;  // DIKS: [stream][spin][t]
+  double dA_l[NSPIN][2], dB_l[NSPIN][2], dA_k[NSPIN][KC], dB_k[NSPIN][KC], dq[KC][2];
   uint32_t off[KC];  // BYTE offset of this lane's pair inside a row, per k of the chunk (same for both streams)
   bool okA[KC], okB[KC];
 #pragma unroll
@@ -218,21 +210,11 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
         (okA[t] || okB[t]) ? __ldg(reinterpret_cast<const double2*>(dq2 + o)) : make_double2(0.0, 0.0);
     dq[t][0] = q2.x;
     dq[t][1] = q2.y;
-    if (!DIKS) {
 #pragma unroll
-      for (int s = 0; s < NSPIN; ++s) {
-        dA_k[s][t] = __ldg(D + s * dstride + (size_t)iA * n + kc);
-        dB_k[s][t] = __ldg(D + s * dstride + (size_t)iT * n + kc);
-      }
+    for (int s = 0; s < NSPIN; ++s) {
+      dA_k[s][t] = __ldg(D + s * dstride + (size_t)iA * n + kc);
+      dB_k[s][t] = __ldg(D + s * dstride + (size_t)iT * n + kc);
     }
-  }
-  if (DIKS) {  // lane -> (stream, spin, t); 2 * NK <= 32
-    if (lane < 2 * NK) {
-      const int st = lane / NK, r = lane - st * NK, s = r / KC, t = r - s * KC;
-      const int kc = k0 + t <= iT ? k0 + t : iT;
-      dik[lane] = __ldg(D + s * dstride + (size_t)(st ? iT : iA) * n + kc);
-    }
-    __syncwarp();
   }
 
   double a1A[NSPIN][KC], a1B[NSPIN][KC], a2A[NSPIN][2], a2B[NSPIN][2], jq[KC][2];
@@ -320,7 +302,7 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
 
   auto flush_tile = [&](int n_rows) {
     __syncwarp();
-    if (red_r < n_rows) {  // (red_r < FR always holds for lanes < FR*NV)
+    if (red_r < n_rows) {  // (red_r < DEPTH always holds for lanes < DEPTH*NV)
       const double2* src = reinterpret_cast<const double2*>(ys + lane * YS);
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -360,7 +342,7 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
     double z[NSPIN][2];
 #pragma unroll
     for (int s = 0; s < NSPIN; ++s) z[s][0] = z[s][1] = 0.0;
-    double* park = ys + (stage % FR) * NV * YS + lane;
+    double* park = ys + stage * NV * YS + lane;
 #pragma unroll
     for (int t = 0; t < KC; t += 2) {
       double2 wA[2], wB[2];
@@ -369,15 +351,9 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
         wA[u] = ring[((stage * 2 + 0) * KC + t + u) * 32];
         wB[u] = ring[((stage * 2 + 1) * KC + t + u) * 32];
       }
-      double2 dk2[NSPIN], dak2[NSPIN], dbk2[NSPIN];
+      double2 dk2[NSPIN];
 #pragma unroll
-      for (int s = 0; s < NSPIN; ++s) {
-        dk2[s] = *reinterpret_cast<const double2*>(dk + s * KC + t);
-        if (DIKS) {  // broadcast reads of the item constants
-          dak2[s] = *reinterpret_cast<const double2*>(dik + s * KC + t);
-          dbk2[s] = *reinterpret_cast<const double2*>(dik + NK + s * KC + t);
-        }
-      }
+      for (int s = 0; s < NSPIN; ++s) dk2[s] = *reinterpret_cast<const double2*>(dk + s * KC + t);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const double x0 = wA[u].x, x1 = wA[u].y, y0 = wB[u].x, y1 = wB[u].y;
@@ -403,12 +379,10 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
           // -> K'[j,k]: both streams feed the same output
           park[(s * KC + t + u) * YS] =
               fma(y1, dB_l[s][1], fma(y0, dB_l[s][0], fma(x1, dA_l[s][1], x0 * dA_l[s][0])));
-          const double dak = DIKS ? (u ? dak2[s].y : dak2[s].x) : dA_k[s][DIKS ? 0 : t + u];
-          const double dbk = DIKS ? (u ? dbk2[s].y : dbk2[s].x) : dB_k[s][DIKS ? 0 : t + u];
-          z[s][0] = fma(x0, dak, z[s][0]);
-          z[s][0] = fma(y0, dbk, z[s][0]);
-          z[s][1] = fma(x1, dak, z[s][1]);
-          z[s][1] = fma(y1, dbk, z[s][1]);
+          z[s][0] = fma(x0, dA_k[s][t + u], z[s][0]);
+          z[s][0] = fma(y0, dB_k[s][t + u], z[s][0]);
+          z[s][1] = fma(x1, dA_k[s][t + u], z[s][1]);
+          z[s][1] = fma(y1, dB_k[s][t + u], z[s][1]);
         }
       }
     }
@@ -452,11 +426,9 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
       commit();
       wait_row();
       consume(d);
-      if ((d + 1) % FR == 0) {
-        flush_tile(FR);
-        j_tile = jc;
-      }
     }
+    flush_tile(DEPTH);
+    j_tile = jc;
     remaining -= DEPTH;
   }
   if (remaining > 0) {  // every remaining row pair is already in flight
@@ -466,13 +438,9 @@ __device__ __forceinline__ void packed_item(const double* __restrict__ eri_a,  /
         commit();
         wait_row();
         consume(d);
-        if ((d + 1) % FR == 0) {
-          flush_tile(FR);
-          j_tile = jc;
-        }
       }
     }
-    if (remaining % FR) flush_tile(remaining % FR);
+    flush_tile(remaining);
   }
 
   // per-item outputs
@@ -808,8 +776,6 @@ static int launch_packed_cfg(scfb_handle_s* h, double* Jp, double* Kp, size_t ds
 template <int NSPIN, bool VECD>
 static int launch_packed(scfb_handle_s* h, double* Jp, double* Kp, size_t dstride) {
   if (NSPIN == 1) return launch_packed_cfg<1, 8, 2, 8, VECD>(h, Jp, Kp, dstride, 0);
-  static const int kc8 = std::getenv("SCFB_PK_UHF_KC8") ? std::atoi(std::getenv("SCFB_PK_UHF_KC8")) : 0;  // EXPERIMENT
-  if (kc8) return launch_packed_cfg<2, 8, 2, 8, VECD>(h, Jp, Kp, dstride, 1);
   return launch_packed_cfg<2, 4, 2, 8, VECD>(h, Jp, Kp, dstride, 1);
 }
 
