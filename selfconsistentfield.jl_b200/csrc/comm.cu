@@ -83,6 +83,9 @@ int scfb_comm_init(scfb_handle_t h, const char* id128) {
   if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
   SCFB_REQUIRE(h, id128, "null id buffer");
   if (h->n_ranks == 1) return SCFB_OK;  // nothing to exchange
+  if (h->multi || scfb_peer_ready(h))
+    return scfb_fail(h, SCFB_ERR_STATE, "this handle already has a peer-memory exchange (scfb_create_multi / "
+                     "scfb_peer_import); a second one cannot be added");
   if (int rc = load_nccl(h)) return rc;
   SCFB_CUDA(h, cudaSetDevice(h->device));
   ncclUniqueId id;
