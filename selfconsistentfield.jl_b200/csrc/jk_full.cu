@@ -275,10 +275,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 constexpr int TMA_MAX_STAGES = 4;
-// position of a work item's partial rows in kpart / jpart (the order k_reduce_kernel sums in)
-__device__ __forceinline__ size_t item_index(int chunk, int slab, int bz, int n_chunks, int BS) {
-  return ((size_t)slab * n_chunks + chunk) * BS + bz;
+
+// Timeline probe of the persistent kernel (tuning builds only: -DSCFB_K1_TRACE, see
+// benchmarks/k1_trace.py).  Off by default: the shipped kernel carries none of it.
+#ifdef SCFB_K1_TRACE
+__device__ unsigned long long g_k1_trace[1024][8];
+__device__ __forceinline__ unsigned long long k1_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
+#define K1_TRACE(slot, val) do { if (tid == 0 && blockIdx.x < 1024) g_k1_trace[blockIdx.x][slot] = (val); } while (0)
+#else
+#define K1_TRACE(slot, val) do { } while (0)
+#endif
 __host__ __device__ inline size_t tma_stage_doubles(int n, int G, int n_spin) {
   return (size_t)(TC + 1) * G * n + (size_t)G * n_spin * TC;
 }
@@ -296,11 +306,12 @@ __global__ void __launch_bounds__(MAX_THREADS + 32 * TMA_PRODUCERS, 2)
 jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dtot,
                    const double* __restrict__ dens, double* __restrict__ jk,
                    double* __restrict__ kpart, double* __restrict__ jpart, int n, int nu_lo, int R,
-                   int G, int S, int n_chunks, int n_slabs, int BS, int* __restrict__ sched,
-                   int* __restrict__ slab_done, unsigned int* __restrict__ grid_done, ScfbFuse fuse) {
+                   int G, int S, int n_chunks, int n_slabs, int whole_slabs, int BSB, int* __restrict__ sched,
+                   int* __restrict__ slab_done, int* __restrict__ grp_done, unsigned int* __restrict__ grid_done,
+                   ScfbFuse fuse) {
   extern __shared__ __align__(128) double ring[];  // [S][stage]
   __shared__ double jred[MAX_THREADS / 32][TC];
-  __shared__ int slab_last;
+  __shared__ int slab_last, grp_last;
   __shared__ uint64_t full[TMA_MAX_STAGES], empty[TMA_MAX_STAGES];
   // Work items are handed out dynamically (SMs do not all stream at the same rate: a static
   // round-robin was 6 % slower than one CTA per item).  Lane 0 of producer warp 0 draws the CTA's
@@ -314,10 +325,21 @@ jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dt
   const int warp = tid >> 5, lane = tid & 31;
   const bool producer = warp >= CW;
   const size_t n2 = (size_t)n * n;
-  const int nb = (n + BS - 1) / BS;
   const size_t stage_doubles = tma_stage_doubles(n, G, NSPIN);
   const int Gn = G * n;
-  const int n_items = n_chunks * n_slabs * BS;
+  // Items [0, n_whole): (chunk, slab) of the first `whole_slabs` slabs, all b.  Items beyond: the
+  // remaining slabs cut BSB ways along b, (bz, chunk, slab) with bz fastest — the END of the
+  // counter hands out pieces 1/BSB the size, so the CTAs run dry within a fraction of an item of
+  // each other instead of within a whole one.  n % BSB == 0 (host), so no piece is empty.
+  const int n_whole = whole_slabs * n_chunks;
+  const int n_items = n_whole + (n_slabs - whole_slabs) * n_chunks * BSB;
+  const int nb_split = n / BSB;
+#ifdef SCFB_K1_TRACE
+  K1_TRACE(0, k1_now());  // CTA start
+  unsigned long long tr_epi = 0, tr_fin = 0, tr_last_start = 0;
+  unsigned int tr_items = 0, tr_smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(tr_smid));
+#endif
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
@@ -372,11 +394,15 @@ jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dt
       for (int k = 0;; ++k) {
         const int item = pw == 0 ? publish_item(k) : fetch_item(k);
         if (item < 0) break;
-        const int chunk = item % n_chunks, rest = item / n_chunks;
-        const int slab = rest % n_slabs, bz = rest / n_slabs;
+        int chunk, slab, b_lo, b_hi;
+        if (item < n_whole) {
+          chunk = item % n_chunks, slab = item / n_chunks, b_lo = 0, b_hi = n;
+        } else {
+          const int j = item - n_whole, bz = j % BSB, cs = j / BSB;
+          chunk = cs % n_chunks, slab = whole_slabs + cs / n_chunks, b_lo = bz * nb_split, b_hi = b_lo + nb_split;
+        }
         const int c0 = chunk * TC;
         const int tcn = min(TC, n - c0);
-        const int b_lo = bz * nb, b_hi = min(n, b_lo + nb);
         const int n_iter = (b_hi - b_lo + G - 1) / G;
         const double* xbase = eri + ((size_t)slab * n + c0) * n2 + (size_t)b_lo * n;  // plane c0, row b_lo
         const int n_jobs = tcn + 1 + G * NSPIN;
@@ -453,11 +479,16 @@ jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dt
   for (int k = 0;; ++k) {
     const int item = fetch_item(k);
     if (item < 0) break;
-    const int chunk = item % n_chunks, rest = item / n_chunks;
-    const int slab = rest % n_slabs, bz = rest / n_slabs;
+    int chunk, slab, b_lo, b_hi;
+    const bool split = item >= n_whole;
+    if (!split) {
+      chunk = item % n_chunks, slab = item / n_chunks, b_lo = 0, b_hi = n;
+    } else {
+      const int j = item - n_whole, bz = j % BSB, cs = j / BSB;
+      chunk = cs % n_chunks, slab = whole_slabs + cs / n_chunks, b_lo = bz * nb_split, b_hi = b_lo + nb_split;
+    }
     const int c0 = chunk * TC;
     const int tcn = min(TC, n - c0);
-    const int b_lo = bz * nb, b_hi = min(n, b_lo + nb);
     const int n_iter = (b_hi - b_lo + G - 1) / G;
 
     double jacc[TC];
@@ -470,8 +501,15 @@ jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dt
     int b = b_lo + g;
     double* last_stage = nullptr;  // the item's last stage doubles as kred before it is released
     int last_slot = 0;
+#ifdef SCFB_K1_TRACE
+    tr_last_start = k1_now();
+    ++tr_items;
+#endif
     for (int it = 0; it < n_iter; ++it) {
       mbar_wait(full + s, parity);
+#ifdef SCFB_K1_TRACE
+      if (k == 0 && it == 0) K1_TRACE(1, k1_now());  // first stage landed
+#endif
       const bool live = active && b < b_hi;
       if (live) {
         // two half-chunks of four planes: 16 operand registers live instead of 32
@@ -522,18 +560,10 @@ jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dt
       }
     }
 
-    if (n_iter == 0) {  // empty b-range of a split item: its partials are zero, no stage was used
-      if (tid < tcn) {
-        if (BS == 1)
-          jk[(size_t)(nu_lo + slab) * n + c0 + tid] = 0.0;
-        else
-          jpart[(size_t)item_index(chunk, slab, bz, n_chunks, BS) * TC + tid] = 0.0;
-      }
-      for (int i = tid; i < NSPIN * n; i += MAX_THREADS)
-        kpart[(size_t)item_index(chunk, slab, bz, n_chunks, BS) * NSPIN * n + i] = 0.0;
-      continue;
-    }
     // ---- item epilogue (as in jk_full_stream_kernel; kred lives in the item's last stage) ----
+#ifdef SCFB_K1_TRACE
+    const unsigned long long tr_e0 = k1_now();
+#endif
     double* kred = last_stage;  // [G][NSPIN][n]
 #pragma unroll
     for (int t = 0; t < TC; ++t) {
@@ -552,12 +582,12 @@ jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dt
     if (tid < tcn) {
       double v = 0.0;
       for (int w = 0; w < CW; ++w) v += jred[w][tid];
-      if (BS == 1)
+      if (!split)
         jk[(size_t)(nu_lo + slab) * n + c0 + tid] = v;
       else
-        jpart[(size_t)item_index(chunk, slab, bz, n_chunks, BS) * TC + tid] = v;
+        jpart[(size_t)(item - n_whole) * TC + tid] = v;
     }
-    double* kp = kpart + (size_t)item_index(chunk, slab, bz, n_chunks, BS) * NSPIN * n;
+    double* kp = kpart + (size_t)item * NSPIN * n;  // one partial row pair per item, in item order
     if (G > 1) {
       asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
       for (int i = tid; i < NSPIN * n; i += MAX_THREADS) {
@@ -580,45 +610,98 @@ jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dt
 
     // ---- fused tail: the CTA that completes a nu-slab reduces it, accumulates / ships it ----
     // (the producers are already streaming the next item; "last block" pattern: every writer
-    // fences, one thread counts, the CTA that sees the last count reads the partials back from L2)
-    if (BS == 1) {
-      __threadfence();
-      asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
+    // fences, one thread counts, the CTA that sees the last count reads the partials back from L2.
+    // A split item first completes its (slab, chunk) group: the last of the BSB pieces folds the
+    // group's rows into the first one and its J partials into J, then counts for the slab like a
+    // whole item.  Every sum runs in a fixed order: the result does not depend on who finishes.)
+    const size_t stride = (size_t)NSPIN * n;
+    __threadfence();
+    asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
+    if (split) {
+      const int grp = (item - n_whole) / BSB;
       if (tid == 0) {
-        const int last = atomicAdd(slab_done + slab, 1) == n_chunks - 1;
-        if (last) slab_done[slab] = 0;  // ready for the next build
-        slab_last = last;
+        const int last = atomicAdd(grp_done + grp, 1) == BSB - 1;
+        if (last) grp_done[grp] = 0;  // ready for the next build
+        grp_last = last;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
-      if (slab_last) {
+      if (grp_last) {
         __threadfence();
-        const size_t col = (size_t)(nu_lo + slab) * n;
-        const size_t stride = (size_t)NSPIN * n;
+        double* row0 = kpart + (size_t)(n_whole + grp * BSB) * stride;
         for (int i = tid; i < NSPIN * n; i += MAX_THREADS) {
-          const int sp = i >= n ? 1 : 0, a = i - sp * n;
-          const double* p = kpart + (size_t)slab * n_chunks * stride + i;
           double v = 0.0;
-          int c = 0;
-          for (; c + 8 <= n_chunks; c += 8) {  // eight loads in flight, added in the same fixed order
-            double t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = __ldcg(p + (size_t)(c + u) * stride);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v += t[u];
-          }
-          for (; c < n_chunks; ++c) v += __ldcg(p + (size_t)c * stride);
-          const double jv = __ldcg(jk + col + a);  // J[a, nu]: written by this slab's items
-          jk[(size_t)(1 + sp) * n2 + col + a] = v;
-          if (fuse.out) fuse.out[(size_t)sp * n2 + col + a] += jv - v;
-          for (int r = 0; r < fuse.n_peers; ++r) {  // plain stores into every rank's landing zone (NVLink)
-            fuse.peer_jk[r][(size_t)(1 + sp) * n2 + col + a] = v;
-            if (sp == 0) fuse.peer_jk[r][col + a] = jv;
-          }
+          for (int z = 0; z < BSB; ++z) v += __ldcg(row0 + (size_t)z * stride + i);
+          row0[i] = v;
         }
-        if (fuse.n_peers) __threadfence_system();
+        if (tid < tcn) {
+          double v = 0.0;
+          for (int z = 0; z < BSB; ++z) v += __ldcg(jpart + (size_t)(grp * BSB + z) * TC + tid);
+          jk[(size_t)(nu_lo + slab) * n + c0 + tid] = v;
+        }
+        __threadfence();
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
+    }
+    if (tid == 0) {
+      int last = 0;
+      if (!split || grp_last) {
+        last = atomicAdd(slab_done + slab, 1) == n_chunks - 1;
+        if (last) slab_done[slab] = 0;
+      }
+      slab_last = last;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
+#ifdef SCFB_K1_TRACE
+    const unsigned long long tr_f0 = k1_now();
+    tr_epi += tr_f0 - tr_e0;
+#endif
+    if (slab_last) {
+      __threadfence();
+      const size_t col = (size_t)(nu_lo + slab) * n;
+      // the slab's n_chunks rows: consecutive for whole items, every BSB-th (the folded ones) otherwise
+      const size_t row0 = split ? (size_t)n_whole + (size_t)(slab - whole_slabs) * n_chunks * BSB : (size_t)slab * n_chunks;
+      const size_t rstep = (split ? (size_t)BSB : 1) * stride;
+      for (int i2 = tid; i2 < NSPIN * n / 2; i2 += MAX_THREADS) {  // n is even: a pair never straddles the spins
+        const int i = 2 * i2, sp = i >= n ? 1 : 0, a = i - sp * n;
+        const double* p = kpart + row0 * stride + i;
+        double2 v = make_double2(0.0, 0.0);
+        int c = 0;
+        for (; c + 8 <= n_chunks; c += 8) {  // eight 16-byte loads in flight, added in the same fixed order
+          double2 t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] = __ldcg(reinterpret_cast<const double2*>(p + (size_t)(c + u) * rstep));
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v.x += t[u].x, v.y += t[u].y;
+        }
+        for (; c < n_chunks; ++c) {
+          const double2 t = __ldcg(reinterpret_cast<const double2*>(p + (size_t)c * rstep));
+          v.x += t.x, v.y += t.y;
+        }
+        const double2 jv = __ldcg(reinterpret_cast<const double2*>(jk + col + a));  // J[a, nu]: written by this slab's items
+        *reinterpret_cast<double2*>(jk + (size_t)(1 + sp) * n2 + col + a) = v;
+        if (fuse.out) {
+          double* o = fuse.out + (size_t)sp * n2 + col + a;  // (caller's pointer: no alignment assumed)
+          o[0] += jv.x - v.x;
+          o[1] += jv.y - v.y;
+        }
+        for (int r = 0; r < fuse.n_peers; ++r) {  // plain stores into every rank's landing zone (NVLink)
+          *reinterpret_cast<double2*>(fuse.peer_jk[r] + (size_t)(1 + sp) * n2 + col + a) = v;
+          if (sp == 0) *reinterpret_cast<double2*>(fuse.peer_jk[r] + col + a) = jv;
+        }
+      }
+      if (fuse.n_peers) __threadfence_system();
+#ifdef SCFB_K1_TRACE
+      tr_fin += k1_now() - tr_f0;
+#endif
     }
   }
+#ifdef SCFB_K1_TRACE
+  K1_TRACE(2, k1_now());  // left the item loop
+  K1_TRACE(4, (unsigned long long)tr_items | ((unsigned long long)tr_smid << 32));
+  K1_TRACE(5, tr_epi);
+  K1_TRACE(6, tr_last_start);
+  K1_TRACE(7, tr_fin);
+#endif
 
   // ---- kernel tail: the last CTA re-arms the counters and publishes this rank's epoch ----
   asm volatile("bar.sync 1, %0;" ::"n"(MAX_THREADS) : "memory");
@@ -634,6 +717,7 @@ jk_full_tma_kernel(const double* __restrict__ eri, const double* __restrict__ dt
       }
     }
   }
+  K1_TRACE(3, k1_now());  // CTA end
 }
 
 // K[a, nu, s] = sum over (chunk, b-split) of the partial rows; with b-splits also
@@ -714,12 +798,9 @@ cudaError_t launch_tma(scfb_handle_s* h, const double* d_density, const double* 
     fprintf(stderr, "[scfb] jk_full_tma_kernel<%d>: n=%d R=%d G=%d stages=%d smem=%zu B threads=%d CTAs/SM=%d "
             "(%d without dynamic smem)\n", NSPIN, n, R, G, S, smem, MAX_THREADS + 32 * TMA_PRODUCERS, occ, occ0);
   }
-  const long items = (long)n_chunks * n_slabs * h->b_splits;
-  if (h->n_sm == 0) {
-    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
-    if (h->n_sm <= 0) h->n_sm = 148;
-  }
-  const int n_sm = h->n_sm;
+  const ScfbFullPlan& pl = h->plan;
+  const long items = (long)n_chunks * (pl.whole_slabs + (long)(n_slabs - pl.whole_slabs) * pl.tail_bs);
+  const int n_sm = h->n_sm > 0 ? h->n_sm : 148;
   static const int per_sm = [] {  // SCFB_FULL_TMA_CTAS=0: one CTA per item (non-persistent), else CTAs per SM
     const char* v = std::getenv("SCFB_FULL_TMA_CTAS");
     return v ? std::atoi(v) : 2;
@@ -729,7 +810,7 @@ cudaError_t launch_tma(scfb_handle_s* h, const double* d_density, const double* 
   // (the work-item counter and the completion counters are re-armed by the kernel's last CTA)
   jk_full_tma_kernel<NSPIN><<<grid, MAX_THREADS + 32 * TMA_PRODUCERS, smem, h->stream>>>(
       h->eri, d_total, d_density, h->jk, h->kpart, h->jpart, n, h->nu_lo, R, G, S, n_chunks, n_slabs,
-      h->b_splits, h->sched, h->slab_done, h->grid_done, fuse);
+      pl.whole_slabs, pl.tail_bs, h->sched, h->slab_done, h->grp_done, h->grid_done, fuse);
   return cudaGetLastError();
 }
 
@@ -744,7 +825,7 @@ cudaError_t launch_stream(scfb_handle_s* h, const double* d_density, const doubl
   if (G > n) G = n;
   const int threads = ((R * G + 31) / 32) * 32;
   const size_t smem = G > 1 ? (size_t)G * NSPIN * n * sizeof(double) : 0;
-  dim3 grid(n_chunks, n_slabs, h->b_splits);
+  dim3 grid(n_chunks, n_slabs, h->plan.b_splits);
   jk_full_stream_kernel<VEC, NSPIN, MAXT><<<grid, threads, smem, h->stream>>>(
       h->eri, d_total, d_density, h->jk, h->kpart, h->jpart, n, h->nu_lo, R, G);
   return cudaGetLastError();
@@ -752,39 +833,71 @@ cudaError_t launch_stream(scfb_handle_s* h, const double* d_density, const doubl
 
 }  // namespace
 
+#ifdef SCFB_K1_TRACE
+extern "C" int scfb_debug_k1_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_k1_trace, sizeof(g_k1_trace));
+}
+#endif
+
 static bool tma_path(int n) {  // the selection rule of scfb_launch_jk_full
   const char* v = std::getenv("SCFB_FULL_TMA");
   return (v ? std::atoi(v) : 1) != 0 && n % 2 == 0 && n >= 8 && n / 2 <= MAX_THREADS;
 }
 
-// b-splits (gridDim.z / the third item coordinate): equal-size work items fill 2 x 148 resident
-// CTA slots in waves, and below ~4 waves the last, partly filled wave costs the LDG kernel > 10 %
-// (n_bf = 256 over 8 GPUs: 1024 items = 3.46 -> 4 waves), so it splits every item over 2-4 CTAs
-// along b.  The persistent TMA kernel hands items out dynamically and pays less per item; there
-// the split only adds partial rows (1/8 shard of n_bf = 256, whole build: 0.650 ms unsplit, 0.663
-// with 2, 0.686 with 4 splits; benchmarks/shard_bsplit.py), so it stays at 1.
-// SCFB_FULL_BSPLIT=1|2|4|8 overrides the rule; read at handle creation (tests, tuning).
-int scfb_full_b_splits(int n, int n_slabs) {
-  const long items = (long)((n + TC - 1) / TC) * n_slabs;
-  if (items <= 0) return 1;
-  if (const char* v = std::getenv("SCFB_FULL_BSPLIT")) {
-    const int forced = std::atoi(v);
-    if (forced > 0) return n / (2 * forced) >= 1 ? forced : 1;
+// Work-item plan of a rank's shard.
+//
+// LDG kernel (one CTA per item): equal-size items fill 2 x n_sm resident CTA slots in waves, and
+// below ~4 waves the last, partly filled wave costs > 10 %, so every (nu, c-chunk) is split over
+// 2-4 CTAs along b (gridDim.z); J then also becomes a per-CTA partial and k_reduce_kernel sums.
+//
+// Persistent TMA kernel: items are drawn from a counter, so only the END of the build is ragged —
+// with whole items (8 planes = 64 n^2 bytes, ~170 us at n_bf = 256) the CTAs run dry up to one item
+// apart (traced on a 1/8 shard of n_bf = 256: 160 of 296 CTAs idle for the last ~95 of 622 us).  The
+// last ~one wave of whole items (ceil(2 n_sm / n_chunks) slabs) is therefore cut tail_bs ways along b
+// into pieces of >= 1 MB; the kernel folds a group's pieces before the slab finisher sees them.
+// SCFB_FULL_BSPLIT=k forces k pieces for EVERY item (both kernels), SCFB_FULL_TAIL=0 keeps all items
+// whole; both are read per handle creation (tests, tuning).
+ScfbFullPlan scfb_full_plan(int n, int n_slabs, int n_sm) {
+  ScfbFullPlan pl;
+  pl.tma = tma_path(n);
+  if (n_slabs <= 0) return pl;
+  if (n_sm <= 0) n_sm = 148;
+  const int n_chunks = (n + TC - 1) / TC;
+  const long items = (long)n_chunks * n_slabs;
+  int forced = 0;
+  if (const char* v = std::getenv("SCFB_FULL_BSPLIT")) forced = std::atoi(v);
+  if (!pl.tma) {
+    int bs = 1;
+    if (forced > 0)
+      bs = n / (2 * forced) >= 1 ? forced : 1;
+    else
+      while (bs < 4 && items * bs < 4L * 2 * n_sm && n / (2 * bs) >= 16) bs *= 2;
+    pl.b_splits = bs;
+    pl.kpart_rows = (uint64_t)items * bs;
+    pl.jpart_rows = bs > 1 ? (uint64_t)items * bs : 0;
+    return pl;
   }
-  if (tma_path(n)) return 1;
-  int bs = 1;
-  while (bs < 4 && items * bs < 4L * 2 * 148 && n / (2 * bs) >= 16) bs *= 2;
-  return bs;
-}
-
-uint64_t scfb_kpart_elems_full(int n, int n_slabs) {
-  const uint64_t n_chunks = (n + TC - 1) / TC;
-  return (uint64_t)n_slabs * n_chunks * scfb_full_b_splits(n, n_slabs) * 2 * n;
-}
-
-uint64_t scfb_jpart_elems_full(int n, int n_slabs) {
-  const uint64_t n_chunks = (n + TC - 1) / TC;
-  return (uint64_t)n_slabs * n_chunks * scfb_full_b_splits(n, n_slabs) * TC;
+  int bs = 1, split_slabs = 0;
+  if (forced > 0) {
+    if (n % forced == 0 && n / forced >= 2) bs = forced, split_slabs = n_slabs;
+  } else {
+    const char* t = std::getenv("SCFB_FULL_TAIL");
+    if (!t || std::atoi(t) != 0) {
+      const size_t item_bytes = (size_t)TC * n * n * sizeof(double);
+      while (bs < 8 && n % (2 * bs) == 0 && item_bytes / (2 * bs) >= ((size_t)1 << 20)) bs *= 2;
+      if (bs > 1) {
+        split_slabs = t && std::atoi(t) > 1 ? std::atoi(t) : (2 * n_sm + n_chunks - 1) / n_chunks;
+        if (split_slabs > n_slabs) split_slabs = n_slabs;
+      }
+    }
+  }
+  if (bs == 1) split_slabs = 0;
+  pl.whole_slabs = n_slabs - split_slabs;
+  pl.tail_bs = bs;
+  pl.n_groups = split_slabs * n_chunks;
+  pl.jpart_rows = (uint64_t)pl.n_groups * bs;
+  pl.kpart_rows = (uint64_t)pl.whole_slabs * n_chunks + pl.jpart_rows;
+  return pl;
 }
 
 // `fuse` (may be null): what the TMA kernel's slab finisher should do beyond filling h->jk;
@@ -796,18 +909,18 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
   const int n_slabs = h->nu_hi - h->nu_lo;
   if (fused) *fused = false;
   if (n_slabs <= 0) {  // this rank owns nothing: its partial stays zero
-    if (h->timed) cudaEventRecord(scfb_ev(h, 3), h->stream);
-    if (h->timed) cudaEventRecord(scfb_ev(h, 1), h->stream);
+    if (h->timed) scfb_ev_alias(h, 3, 0);
+    if (h->timed) scfb_ev_alias(h, 1, 0);
     return SCFB_OK;
   }
   const bool even = (n % 2 == 0);
   // VEC=2 needs R = n/2 <= MAX_THREADS; wider rows fall back to more rows per thread? no:
   // rows longer than 2*MAX_THREADS are rejected at create time.
   cudaError_t e;
-  if (h->timed) cudaEventRecord(scfb_ev(h, 3), h->stream);
+  if (h->timed) scfb_ev_alias(h, 3, 0);  // the stream kernel is the build's first launch
   const bool wide = (even ? n / 2 : n) > MAX_THREADS;  // rows longer than one 256-thread pass
-  const bool tma = tma_path(n);  // SCFB_FULL_TMA=0 selects the register-prefetch (LDG) kernel
-  const bool in_kernel_tail = tma && h->b_splits == 1;
+  const bool tma = h->plan.tma;  // SCFB_FULL_TMA=0 selects the register-prefetch (LDG) kernel
+  const bool in_kernel_tail = tma;  // every slab is finished inside the kernel
   if (tma) {
     ScfbFuse f{};
     if (fuse && in_kernel_tail) {
@@ -830,7 +943,7 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
                     : launch_stream<1, 2, 512>(h, d_density, d_total);
   if (e != cudaSuccess)
     return scfb_fail(h, SCFB_ERR_CUDA, "jk_full_stream_kernel launch: %s", cudaGetErrorString(e));
-  if (h->timed) cudaEventRecord(scfb_ev(h, 1), h->stream);
+  if (h->timed) scfb_ev_record(h, 1);
   if (in_kernel_tail) {  // K rows were reduced by the slab finishers
     h->launches += 1;
     return SCFB_OK;
@@ -840,7 +953,7 @@ int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density,
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   k_reduce_kernel<<<blocks, 256, 0, h->stream>>>(h->kpart, h->jpart, h->jk, n, h->nu_lo, n_slabs,
-                                                 n_chunks, n_spin, h->b_splits);
+                                                 n_chunks, n_spin, h->plan.b_splits);
   e = cudaGetLastError();
   if (e != cudaSuccess)
     return scfb_fail(h, SCFB_ERR_CUDA, "k_reduce_kernel launch: %s", cudaGetErrorString(e));

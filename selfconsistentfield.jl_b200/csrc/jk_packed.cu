@@ -791,7 +791,7 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
   pack_density_kernel<<<n < 296 ? n : 296, 128, 0, h->stream>>>(d_total, d_density, h->pk_dq2, h->pk_dpad, n, n_spin);
   const size_t dstride = n2 + DPAD;
   h->launches += 1;
-  if (h->timed) cudaEventRecord(scfb_ev(h, 3), h->stream);
+  if (h->timed) scfb_ev_record(h, 3);
   if (h->i_hi > h->i_lo) {
     double* Jp = h->pk_acc;
     double* Kp = h->pk_acc + PQ;
@@ -802,7 +802,7 @@ int scfb_launch_jk_packed(scfb_handle_s* h, int n_spin, const double* d_density,
       rc = n_spin == 1 ? launch_packed<1, false>(h, Jp, Kp, dstride) : launch_packed<2, false>(h, Jp, Kp, dstride);
     if (rc) return rc;
   }
-  if (h->timed) cudaEventRecord(scfb_ev(h, 1), h->stream);
+  if (h->timed) scfb_ev_record(h, 1);
   unpack_jk_kernel<<<148 * 2, 256, 0, h->stream>>>(h->pk_acc, h->pk_acc + PQ, h->jk, n, n_spin);
   e = cudaGetLastError();
   if (e != cudaSuccess)

@@ -103,24 +103,35 @@ int scfb_build_jk(scfb_handle_s* h, int n_spin, const double* d_density, const d
     fuse.out = d_out;  // single rank: the slab finishers accumulate, no further launch
   bool fused = false;
   ++h->build_no;
-  if (h->timed) SCFB_CUDA(h, cudaEventRecord(scfb_ev(h, 0), h->stream));
+  if (h->timed) SCFB_CUDA(h, scfb_ev_record(h, 0));
   if (int rc = h->layout == SCFB_LAYOUT_FULL ? scfb_launch_jk_full(h, n_spin, d_density, d_total, &fuse, &fused)
                                              : scfb_launch_jk_packed(h, n_spin, d_density, d_total))
     return rc;
   if (out_event) SCFB_CUDA(h, cudaStreamWaitEvent(h->stream, out_event, 0));
   const double* jk = h->jk;
+  bool tail_work = out_event != nullptr;  // anything enqueued after the layout's own launches?
   if (use_peer) {
     if (int rc = scfb_peer_exchange(h, n_spin, d_out, fused)) return rc;
     jk = h->jk_sum;  // (valid when d_out == nullptr)
+    tail_work = true;
   } else {
     if (use_nccl) {
       if (int rc = scfb_comm_allreduce_jk(h, n_spin)) return rc;
       jk = h->jk_sum;
+      tail_work = true;
     }
-    if (d_out && !(fused && fuse.out))
+    if (d_out && !(fused && fuse.out)) {
       if (int rc = scfb_launch_accumulate(h, n_spin, jk, d_out)) return rc;
+      tail_work = true;
+    }
   }
-  if (h->timed) SCFB_CUDA(h, cudaEventRecord(scfb_ev(h, 2), h->stream));
+  if (h->timed) {
+    // single launch (the fused K1 tail did everything): the build ends where the stream kernel does
+    if (h->layout == SCFB_LAYOUT_FULL && h->plan.tma && !tail_work)
+      scfb_ev_alias(h, 2, 1);
+    else
+      SCFB_CUDA(h, scfb_ev_record(h, 2));
+  }
   if (jk_final) *jk_final = jk;
   return SCFB_OK;
 }
@@ -163,8 +174,6 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
   if (layout == SCFB_LAYOUT_FULL) {
     scfb_split_range(n_bas, rank, n_ranks, &h->nu_lo, &h->nu_hi);
     h->eri_elems = n2 * n * (uint64_t)(h->nu_hi - h->nu_lo);
-    h->kpart_elems = scfb_kpart_elems_full(n_bas, h->nu_hi - h->nu_lo);
-    h->b_splits = scfb_full_b_splits(n_bas, h->nu_hi - h->nu_lo);
   } else {
     scfb_packed_split(n_bas, rank, n_ranks, &h->i_lo, &h->i_hi);
     h->pk_offset = scfb_packed_offset(h->i_lo);
@@ -197,9 +206,16 @@ int scfb_create(scfb_handle_t* out, int n_bas, int layout, int device, int rank,
   CREATE_CUDA(cudaMemsetAsync(h->jk, 0, 3 * n2 * sizeof(double), h->stream));
   h->jk_sum = h->jk;
   if (n_ranks > 1) CREATE_CUDA(cudaMalloc(&h->jk_sum, 3 * n2 * sizeof(double)));
-  if (h->kpart_elems) CREATE_CUDA(cudaMalloc(&h->kpart, h->kpart_elems * sizeof(double)));
-  if (layout == SCFB_LAYOUT_FULL && h->b_splits > 1)
-    CREATE_CUDA(cudaMalloc(&h->jpart, scfb_jpart_elems_full(n_bas, h->nu_hi - h->nu_lo) * sizeof(double)));
+  CREATE_CUDA(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device));
+  if (layout == SCFB_LAYOUT_FULL) {
+    h->plan = scfb_full_plan(n_bas, h->nu_hi - h->nu_lo, h->n_sm);
+    if (h->plan.kpart_rows) CREATE_CUDA(cudaMalloc(&h->kpart, h->plan.kpart_rows * 2 * n * sizeof(double)));
+    if (h->plan.jpart_rows) CREATE_CUDA(cudaMalloc(&h->jpart, h->plan.jpart_rows * 8 * sizeof(double)));
+    if (h->plan.n_groups) {
+      CREATE_CUDA(cudaMalloc(&h->grp_done, h->plan.n_groups * sizeof(int)));
+      CREATE_CUDA(cudaMemsetAsync(h->grp_done, 0, h->plan.n_groups * sizeof(int), h->stream));
+    }
+  }
   CREATE_CUDA(cudaMalloc(&h->sched, 2 * sizeof(int)));  // [work-item counter | finished-CTA counter]
   CREATE_CUDA(cudaMemsetAsync(h->sched, 0, 2 * sizeof(int), h->stream));
   h->grid_done = reinterpret_cast<unsigned int*>(h->sched + 1);
@@ -241,6 +257,7 @@ int scfb_destroy(scfb_handle_t h) {
   cudaFree(h->jpart);
   cudaFree(h->sched);
   cudaFree(h->slab_done);
+  cudaFree(h->grp_done);
   cudaFree(h->pk_acc);
   cudaFree(h->pk_dq2);
   cudaFree(h->pk_dpad);
@@ -520,10 +537,12 @@ int scfb_build_ms_history(scfb_handle_t h, int max_builds, double* stream_ms, do
   if (count == 0) return SCFB_OK;
   SCFB_CUDA(h, cudaEventSynchronize(scfb_ev(h, 2)));
   for (int i = 0; i < count; ++i) {  // oldest first
-    cudaEvent_t* ev = h->ev_ring[(h->build_no - count + i) % SCFB_EV_RING];
+    const int slot = (int)((h->build_no - count + i) % SCFB_EV_RING);
+    cudaEvent_t* ev = h->ev_ring[slot];
+    const unsigned char* m = h->ev_map[slot];
     float a = 0.f, b = 0.f;
-    SCFB_CUDA(h, cudaEventElapsedTime(&a, ev[3], ev[1]));
-    SCFB_CUDA(h, cudaEventElapsedTime(&b, ev[0], ev[2]));
+    SCFB_CUDA(h, cudaEventElapsedTime(&a, ev[m[3]], ev[m[1]]));
+    SCFB_CUDA(h, cudaEventElapsedTime(&b, ev[m[0]], ev[m[2]]));
     if (stream_ms) stream_ms[i] = a;
     if (total_ms) total_ms[i] = b;
   }

@@ -25,6 +25,17 @@ struct ScfbFuse {
   unsigned long long epoch = 0;           // published there by the kernel's last CTA
 };
 
+// How the full-layout kernels cut a rank's nu-slabs into work items (jk_full.cu: scfb_full_plan).
+struct ScfbFullPlan {
+  bool tma = false;          // persistent bulk-copy kernel (else the register-prefetch LDG kernel)
+  int b_splits = 1;          // LDG kernel: CTAs sharing one (nu, c-chunk) along b (gridDim.z)
+  int whole_slabs = 0;       // TMA kernel: the first slabs are handed out as whole (nu, c-chunk) items,
+  int tail_bs = 1;           //   the remaining ones cut tail_bs ways along b (finer items at the end)
+  uint64_t kpart_rows = 0;   // partial K rows ([2][n] doubles each) / partial J rows (TC doubles each)
+  uint64_t jpart_rows = 0;
+  int n_groups = 0;          // split (nu, c-chunk) groups (completion counters)
+};
+
 struct scfb_handle_s {
   int n = 0;             // n_bas
   int layout = SCFB_LAYOUT_FULL;
@@ -53,17 +64,17 @@ struct scfb_handle_s {
   double* d_out = nullptr;      // n*n*2
   double* jk = nullptr;         // [J | K_0 | K_1], 3*n*n, this rank's partial: zero outside owned columns
   double* jk_sum = nullptr;     // allreduce result (n_ranks > 1); == jk when single rank
-  double* kpart = nullptr;      // per-(nu, c-chunk, b-split) partial K rows
-  double* jpart = nullptr;      // per-(nu, c-chunk, b-split) partial J values (b_splits > 1)
+  double* kpart = nullptr;      // partial K rows, one [n_spin][n] row per work item
+  double* jpart = nullptr;      // partial J values of the b-split work items
   int* sched = nullptr;         // work-item counter of the persistent kernels
   int* slab_done = nullptr;     // per owned nu-slab: finished work items of the running build (K1 fused tail)
+  int* grp_done = nullptr;      // per split (nu, c-chunk): finished pieces of the running build
   unsigned int* grid_done = nullptr;  // CTAs of the running K1 launch that have finished
   int n_sm = 0;                 // SM count of this handle's device (lazily queried)
   bool tma_attr[3] = {false, false, false};  // per NSPIN: smem attributes of jk_full_tma_kernel set on this device
   uint2* pk_items[2] = {};   // live work items of jk_packed_kernel per spin count (built at first launch)
   int pk_n_items[2] = {-1, -1};
-  int b_splits = 1;             // CTAs sharing one (nu, c-chunk) work item along b
-  uint64_t kpart_elems = 0;
+  ScfbFullPlan plan;            // how K1 cuts the owned nu-slabs into work items
   double* h_stage = nullptr;    // pinned host staging, 5*n*n
 
   cudaStream_t stream = nullptr;
@@ -72,6 +83,7 @@ struct scfb_handle_s {
   cudaEvent_t ev_side[2] = {nullptr, nullptr};  // [d_out free again, d_out uploaded]
   // CUDA-event timing of the last SCFB_EV_RING builds: [build start, stream-kernel end, build end, stream-kernel start]
   cudaEvent_t ev_ring[SCFB_EV_RING][4] = {};
+  unsigned char ev_map[SCFB_EV_RING][4] = {};  // logical -> recorded event: neighbours with nothing enqueued between them share one record
   uint64_t build_no = 0;  // builds started on this handle; build b uses ring slot b % SCFB_EV_RING
   bool timed = false;
   uint64_t launches = 0;
@@ -88,7 +100,22 @@ struct scfb_handle_s {
 };
 
 // event i of the build in progress (or, between builds, of the last one)
-inline cudaEvent_t scfb_ev(scfb_handle_s* h, int i) { return h->ev_ring[(h->build_no + SCFB_EV_RING - 1) % SCFB_EV_RING][i]; }
+inline int scfb_ev_slot(const scfb_handle_s* h) { return (int)((h->build_no + SCFB_EV_RING - 1) % SCFB_EV_RING); }
+inline cudaEvent_t scfb_ev(scfb_handle_s* h, int i) {
+  const int slot = scfb_ev_slot(h);
+  return h->ev_ring[slot][h->ev_map[slot][i]];
+}
+inline cudaError_t scfb_ev_record(scfb_handle_s* h, int i) {
+  const int slot = scfb_ev_slot(h);
+  h->ev_map[slot][i] = (unsigned char)i;
+  return cudaEventRecord(h->ev_ring[slot][i], h->stream);
+}
+// event i is the same point of the stream as event j (nothing was enqueued in between): an event
+// record costs the GPU front end a few microseconds, which a sub-millisecond build notices
+inline void scfb_ev_alias(scfb_handle_s* h, int i, int j) {
+  const int slot = scfb_ev_slot(h);
+  h->ev_map[slot][i] = h->ev_map[slot][j];
+}
 
 // thread-local message for calls that fail before a handle exists
 extern thread_local char scfb_tls_err[512];
@@ -129,9 +156,7 @@ inline void scfb_split_range(int n, int rank, int n_ranks, int* lo, int* hi) {
 int scfb_launch_jk_full(scfb_handle_s* h, int n_spin, const double* d_density, const double* d_total,
                         const ScfbFuse* fuse, bool* fused);  // fills h->jk for owned columns
 int scfb_launch_accumulate(scfb_handle_s* h, int n_spin, const double* d_jk, double* d_out);  // out += J - K_s
-uint64_t scfb_kpart_elems_full(int n, int n_slabs);
-uint64_t scfb_jpart_elems_full(int n, int n_slabs);
-int scfb_full_b_splits(int n, int n_slabs);
+ScfbFullPlan scfb_full_plan(int n, int n_slabs, int n_sm);
 // jk_packed.cu
 void scfb_packed_split(int n, int rank, int n_ranks, int* i_lo, int* i_hi);
 uint64_t scfb_packed_offset(int i);
