@@ -171,6 +171,13 @@ int scfb_pulay_error(scfb_handle_t h, int n_spin, const double* fock, const doub
                      const double* overlap, double* error_out);
 int scfb_sygvd(scfb_handle_t h, int n_spin, int n_orb, const double* fock, const double* overlap,
                double* orben_out, double* orbcoeff_out);
+/* The eigensolver scfb_scf_roothaan uses for n_bas <= 320 (one-sided Jacobi, the matrix resident in the shared
+ * memory of one CTA or of a cluster of 8; compute_orbitals.jl:14 after the reduction with the cached Cholesky factor of S):
+ * `batch` (1 or 2) symmetric n x n matrices a (n <= 320), column-major and consecutive; v0 = NULL or orthonormal
+ * warm-start bases (eigenvectors of a nearby matrix).  w_out (batch*n) ascending, z_out columns = eigenvectors,
+ * sweeps_out[batch] = Jacobi sweeps taken.  n is independent of the handle's n_bas. */
+int scfb_syev_jacobi(scfb_handle_t h, int n, int batch, const double* a, const double* v0, double* w_out,
+                     double* z_out, int* sweeps_out);
 /* compute_density.jl:4-35: density_out[:,:,s] = C_occ,s C_occ,s' (alpha from block 0, beta from the
  * last of the n_spin_c blocks of orbcoeff (n, n_orb, n_spin_c)); n_densities blocks are written. */
 int scfb_density(scfb_handle_t h, int n_spin_c, int n_densities, int n_occ_a, int n_occ_b, int n_orb,

@@ -182,6 +182,30 @@ class JKBuilderCUDA(TwoElectronBuilder):
                    self._h)
         return a[:cnt.value], b[:cnt.value]
 
+    def syev_jacobi(self, a, v0=None):
+        """Eigen-decomposition of one (n, n) or a stack (batch, n, n) of symmetric matrices with the
+        small-matrix Jacobi kernels the device-resident SCF step uses (n <= 320); `v0`: orthonormal
+        warm-start bases of the same shape.  Returns (w ascending, z with eigenvectors in columns, sweeps)."""
+        a = np.asarray(a, dtype=np.float64)
+        single = a.ndim == 2
+        a3 = a[None] if single else a
+        batch, n, _ = a3.shape
+        # column-major matrices, consecutive: a symmetric matrix is its own transpose; bases are not
+        a_c = np.ascontiguousarray(np.transpose(a3, (0, 2, 1)))
+        v_c = None
+        if v0 is not None:
+            v3 = np.asarray(v0, dtype=np.float64)
+            v3 = v3[None] if single else v3
+            v_c = np.ascontiguousarray(np.transpose(v3, (0, 2, 1)))
+        w = np.zeros((batch, n))
+        z = np.zeros((batch, n, n))
+        sweeps = (C.c_int * batch)()
+        capi.check(capi.lib().scfb_syev_jacobi(self._h, n, batch, capi.ptr(a_c), capi.ptr(v_c) if v_c is not None else None,
+                                               capi.ptr(w), capi.ptr(z), sweeps), self._h)
+        z = np.transpose(z, (0, 2, 1))  # stored column-major
+        sw = list(sweeps)
+        return (w[0], z[0], sw[0]) if single else (w, z, sw)
+
     @property
     def launch_count(self):
         c = C.c_uint64()

@@ -69,6 +69,7 @@ _SIGNATURES = {
     "scfb_scf_get": [_h, C.c_int, _dp],
     "scfb_pulay_error": [_h, C.c_int, _dp, _dp, _dp, _dp],
     "scfb_sygvd": [_h, C.c_int, C.c_int, _dp, _dp, _dp, _dp],
+    "scfb_syev_jacobi": [_h, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.POINTER(C.c_int)],
     "scfb_density": [_h, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp],
     "scfb_fock_assemble": [_h, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp],
     "scfb_comm_unique_id": [C.c_char_p],

@@ -38,7 +38,10 @@ struct scfb_scf_state {
   double* R = nullptr;       // ROHF scratch: [Pc | Po | Pv | Fc | X | Feff], 6 n^2
   double* Lchol = nullptr;   // Cholesky factor of S (lower), computed once (ScfProblem.jl:48-49 TODO)
   int eig_mode = 0;          // 0 = Dsygvd per block (LAPACK path), 1 = cached Cholesky + Dsyevd,
-                             // 2 = cached Cholesky + Jacobi warm-started in the previous step's eigenbasis
+                             // 2 = cached Cholesky + cuSOLVER Jacobi warm-started in the previous step's eigenbasis
+                             // 3 = cached Cholesky + the shared-memory / cluster Jacobi of eig_jacobi.cu (n <= 320)
+  double* Uj = nullptr;      // 2 n^2: (L^-1 F L^-T) Yprev, the input of mode 3
+  int* jsweeps = nullptr;    // 2 ints: sweeps the last mode-3 solve took per spin block
   double* work_ev = nullptr;  // Dsyevd / Dsyevj workspace
   int lwork_ev = 0;
   double* Yprev = nullptr;   // 2 n^2: orthonormal eigenvectors of L^-1 F L^-T of the previous step
@@ -260,9 +263,10 @@ int rohf_effective_fock(scfb_handle_s* h, scfb_scf_state* st, const double* F2, 
 
 // Orbitals of the iterate F (n_spin blocks) into st->C / st->eps (compute_orbitals.jl:14): LAPACK
 // sygvd semantics (C' S C = I, ascending eps).  eig_mode 0: cusolverDnDsygvd per block.  eig_mode
-// 1/2: S = L L' was factored once at setup, so a block costs A = L^-1 F L^-T (two Dtrsm), a
-// standard symmetric eigensolve (Dsyevd per block, or ONE batched syev for both spin blocks) and
-// C = L^-T Y (one Dtrsm).
+// 1/2/3: S = L L' was factored once at setup, so a block costs A = L^-1 F L^-T (two Dtrsm), a
+// standard symmetric eigensolve (Dsyevd per block; cuSOLVER's Jacobi in the previous step's
+// eigenbasis; or, mode 3, ONE launch of eig_jacobi.cu for both spin blocks, warm-started the same
+// way) and C = L^-T Y (one Dtrsm).
 int solve_orbitals(scfb_handle_s* h, scfb_scf_state* st) {
   const int n = st->n, ns = st->n_spin;
   const size_t n2 = (size_t)n * n;
@@ -292,6 +296,7 @@ int solve_orbitals(scfb_handle_s* h, scfb_scf_state* st) {
     SCFB_BLAS(h, cublasDtrsm(st->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
                              n, n, &one, st->Lchol, n, A, n));  // A <- A L^-T
     h->launches += 2;
+    if (st->eig_mode == 3) continue;  // both blocks are solved by one launch below
     if (st->eig_mode == 1) {
       SCFB_SOLVER(h, cusolverDnDsyevd(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, A, n,
                                       st->eps + s * n, st->work_ev, st->lwork_ev, st->dev_info));
@@ -321,6 +326,29 @@ int solve_orbitals(scfb_handle_s* h, scfb_scf_state* st) {
     SCFB_BLAS(h, cublasDtrsm(st->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, n,
                              n, &one, st->Lchol, n, A, n));  // C <- L^-T Y
     h->launches += 1;
+  }
+  if (st->eig_mode == 3) {
+    // U = A Yprev: in the previous step's eigenbasis the columns are nearly orthogonal already
+    const bool warm = st->have_y[0];
+    if (warm) {
+      for (int s = 0; s < ns; ++s)
+        if (int rc = gemm(h, st, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, 1.0, st->C + s * n2, n, st->Yprev + s * n2, n, 0.0,
+                          st->Uj + s * n2, n))
+          return rc;
+    } else {
+      SCFB_CUDA(h, cudaMemcpyAsync(st->Uj, st->C, n2 * ns * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    SCFB_CUDA(h, cudaMemsetAsync(st->dev_info, 0, sizeof(int), h->stream));
+    if (int rc = scfb_launch_jacobi_eig(h, n, ns, st->Uj, warm ? st->Yprev : nullptr, st->C, st->eps, st->dev_info,
+                                        st->jsweeps))
+      return rc;
+    SCFB_CUDA(h, cudaMemcpyAsync(st->Yprev, st->C, n2 * ns * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    st->have_y[0] = st->have_y[1] = true;
+    for (int s = 0; s < ns; ++s) {
+      SCFB_BLAS(h, cublasDtrsm(st->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, n,
+                               n, &one, st->Lchol, n, st->C + s * n2, n));  // C <- L^-T Y
+      h->launches += 1;
+    }
   }
   return SCFB_OK;
 }
@@ -358,8 +386,9 @@ void scfb_scf_free(scfb_handle_s* h) {
   if (!st) return;
   for (double* p : {st->S, st->H, st->F, st->Fnew, st->D, st->Dtot, st->G, st->E, st->C, st->eps,
                     st->T1, st->T2, st->Bw, st->work, st->scal, st->coef, st->Fh, st->Eh, st->Dh,
-                    st->Cprev, st->epsprev, st->Dprev, st->R, st->Lchol, st->work_ev, st->Yprev})
+                    st->Cprev, st->epsprev, st->Dprev, st->R, st->Lchol, st->work_ev, st->Yprev, st->Uj})
     cudaFree(p);
+  cudaFree(st->jsweeps);
   if (st->jw) cusolverDnDestroySyevjInfo(st->jw);
   cudaFree(st->dev_info);
   cudaFree(st->work_j);
@@ -397,10 +426,13 @@ int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core,
   int want_eig;
   {
     const char* eig = std::getenv("SCFB_EIG");
-    // default (same-box timings in profiles/README.md): the warm-started Jacobi wins while the matrices are
-    // small (n_bf = 128: 2.9 vs 3.6 ms per RHF iteration, 3.1 vs 5.6 UHF), Dsyevd on the cached factor beyond
-    want_eig = !eig ? (n < 200 ? 2 : 1)
-                    : (std::strcmp(eig, "syevd") == 0 ? 1 : (std::strcmp(eig, "warm") == 0 ? 2 : 0));
+    // default (same-box timings in profiles/README.md): the warm-started Jacobi kernels of eig_jacobi.cu up to
+    // n_bf = 320, Dsyevd on the cached factor beyond.  RHF iteration at n_bf = 128: Dsygvd 3.5 ms, Dsyevd on the
+    // cached factor 3.6, cuSOLVER's Jacobi warm-started 2.4, eig_jacobi.cu 1.3; at n_bf = 256: Dsyevd 8.3, eig_jacobi.cu 7.7.
+    const int native_ok = n <= scfb_jacobi_eig_max_n();
+    want_eig = !eig ? (native_ok ? 3 : 1)
+                    : (std::strcmp(eig, "syevd") == 0 ? 1
+                       : (std::strcmp(eig, "warm") == 0 ? 2 : (std::strcmp(eig, "native") == 0 && native_ok ? 3 : 0)));
   }
   const bool want_jacobi = [] { const char* e = std::getenv("SCFB_EIG"); return e && std::strcmp(e, "jacobi") == 0; }();
   scfb_scf_state* st = h->scf;
@@ -460,7 +492,11 @@ int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core,
     st->eig_mode = want_eig;  // SCFB_EIG = sygvd | syevd | warm | jacobi (see solve_orbitals)
     if (st->eig_mode != 0) {
       SCFB_CUDA(h, alloc(&st->Lchol, n2));
-      if (st->eig_mode == 1) {
+      if (st->eig_mode == 3) {
+        SCFB_CUDA(h, alloc(&st->Yprev, 2 * n2));
+        SCFB_CUDA(h, alloc(&st->Uj, 2 * n2));
+        SCFB_CUDA(h, cudaMalloc(&st->jsweeps, 2 * sizeof(int)));
+      } else if (st->eig_mode == 1) {
         SCFB_SOLVER(h, cusolverDnDsyevd_bufferSize(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
                                                    st->T1, n, st->eps, &st->lwork_ev));
       } else {
@@ -608,8 +644,13 @@ int scfb_scf_roothaan(scfb_handle_t h) {
   if (int rc = solve_orbitals(h, st)) return rc;
   int info = 0;
   SCFB_CUDA(h, cudaMemcpyAsync(&info, st->dev_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  static const bool verbose = std::getenv("SCFB_VERBOSE") != nullptr;
+  int sweeps[2] = {0, 0};
+  if (verbose && st->eig_mode == 3)
+    SCFB_CUDA(h, cudaMemcpyAsync(sweeps, st->jsweeps, ns * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (int rc_ = scfb_stream_sync_checked(h)) return rc_;
   if (info != 0) return scfb_fail(h, SCFB_ERR_CUSOLVER, "eigensolver failed: info=%d", info);
+  if (verbose && st->eig_mode == 3) fprintf(stderr, "[scfb] jacobi_eig_kernel: %d / %d sweeps\n", sweeps[0], sweeps[1]);
   // D_s = C[:, 1:n_elec[s], s'] C[...]'   (compute_density.jl:16-32; ROHF: both densities from the one orbital block)
   for (int s = 0; s < nd; ++s) {
     const int nocc = st->n_elec[s];
@@ -840,6 +881,51 @@ int scfb_sygvd(scfb_handle_t h, int n_spin, int n_orb, const double* fock, const
   if (rc) return rc;
   if (e != cudaSuccess) return scfb_fail(h, e == cudaErrorMemoryAllocation ? SCFB_ERR_OOM : SCFB_ERR_CUDA,
                                          "sygvd: %s", cudaGetErrorString(e));
+  return SCFB_OK;
+}
+
+// Stateless twin of the small-matrix eigensolver the device-resident SCF step uses (eig_jacobi.cu):
+// `batch` symmetric n x n matrices (column-major, consecutive), optional orthonormal warm-start
+// bases v0 (the eigenvectors of a nearby matrix).  Eigenvalues ascending, eigenvectors in columns.
+int scfb_syev_jacobi(scfb_handle_t h, int n, int batch, const double* a, const double* v0, double* w_out,
+                     double* z_out, int* sweeps_out) {
+  if (!h) return scfb_fail(nullptr, SCFB_ERR_ARG, "null handle");
+  SCFB_REQUIRE(h, a && w_out && z_out && batch >= 1 && batch <= 2, "bad arguments");
+  SCFB_REQUIRE(h, n >= 1 && n <= scfb_jacobi_eig_max_n(), "n=%d outside [1, %d]", n, scfb_jacobi_eig_max_n());
+  SCFB_CUDA(h, cudaSetDevice(h->device));
+  if (int rc0 = ensure_dense_handles(h)) return rc0;
+  const size_t n2 = (size_t)n * n;
+  double* buf = nullptr;
+  int* idev = nullptr;
+  SCFB_CUDA(h, cudaMalloc(&buf, (4 * n2 + n) * batch * sizeof(double)));
+  cudaError_t e = cudaMalloc(&idev, 3 * sizeof(int));
+  double *A = buf, *V = A + batch * n2, *U = V + batch * n2, *Z = U + batch * n2, *W = Z + batch * n2;
+  int rc = SCFB_OK, host_i[3] = {0, 0, 0};
+  if (e == cudaSuccess) e = cudaMemsetAsync(idev, 0, 3 * sizeof(int), h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(A, a, batch * n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess && v0) {
+    e = cudaMemcpyAsync(V, v0, batch * n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    const double one = 1.0, zero = 0.0;
+    for (int b = 0; b < batch && e == cudaSuccess && rc == SCFB_OK; ++b)
+      if (cublasDgemm(static_cast<cublasHandle_t>(h->blas), CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, &one, A + b * n2, n,
+                      V + b * n2, n, &zero, U + b * n2, n) != CUBLAS_STATUS_SUCCESS)
+        rc = scfb_fail(h, SCFB_ERR_CUSOLVER, "Dgemm failed");
+  }
+  if (e == cudaSuccess && rc == SCFB_OK)
+    rc = scfb_launch_jacobi_eig(h, n, batch, v0 ? U : A, v0 ? V : nullptr, Z, W, idev, idev + 1);
+  if (e == cudaSuccess && rc == SCFB_OK) {
+    cudaMemcpyAsync(host_i, idev, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(w_out, W, (size_t)batch * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(z_out, Z, batch * n2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    e = cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(idev);
+  cudaFree(buf);
+  if (rc) return rc;
+  if (e != cudaSuccess) return scfb_fail(h, SCFB_ERR_CUDA, "syev_jacobi: %s", cudaGetErrorString(e));
+  if (host_i[0] != 0) return scfb_fail(h, SCFB_ERR_CUSOLVER, "Jacobi eigensolver did not converge (info=%d)", host_i[0]);
+  if (sweeps_out)
+    for (int b = 0; b < batch; ++b) sweeps_out[b] = host_i[1 + b];
   return SCFB_OK;
 }
 

@@ -186,6 +186,10 @@ int scfb_multi_inputs_consumed(scfb_handle_s* h0);
 // comm.cu
 int scfb_comm_allreduce_jk(scfb_handle_s* h, int n_spin);
 int scfb_comm_destroy(scfb_handle_s* h);
+// eig_jacobi.cu
+int scfb_jacobi_eig_max_n();
+int scfb_launch_jacobi_eig(scfb_handle_s* h, int n, int batch, const double* AV, const double* V0, double* Z, double* W,
+                           int* info, int* sweeps_out);
 // dense.cu
 void scfb_scf_free(scfb_handle_s* h);
 void scfb_dense_handles_destroy(scfb_handle_s* h);

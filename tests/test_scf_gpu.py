@@ -201,7 +201,7 @@ def test_rohf_effective_fock_on_device_matches_oracle(golden_dir):
     assert np.abs(d[:, :, 1] - c[:, :2] @ c[:, :2].T).max() < 1e-12
 
 
-@pytest.mark.parametrize("eig", ["sygvd", "syevd", "warm"])
+@pytest.mark.parametrize("eig", ["sygvd", "syevd", "warm", "native"])
 def test_eigensolver_variants_give_lapack_semantics(eig, monkeypatch):
     """SCFB_EIG: Dsygvd per block, or the overlap's Cholesky factor cached at setup
     (ScfProblem.jl:48-49 TODO) + Dsyevd / warm-started Jacobi: F C = S C eps, C' S C = I, ascending."""
