@@ -100,10 +100,14 @@ __global__ void __launch_bounds__(1024) trace_kernel(TraceBatch batch, int n, do
   const TracePair pr = batch.p[blockIdx.x];
   const size_t n2 = (size_t)n * n;
   double acc = 0.0;
+  // (i, j) of element e = i + j n advance with e: no division inside the loop
+  unsigned i = threadIdx.x % n, j = threadIdx.x / n;
+  const unsigned di = blockDim.x % n, dj = blockDim.x / n;
   for (size_t e = threadIdx.x; e < n2; e += blockDim.x) {
-    const size_t i = e % n, j = e / n;
-    const double bv = pr.transpose_b ? pr.b[j + i * n] : pr.b[e];
+    const double bv = pr.transpose_b ? pr.b[j + (size_t)i * n] : pr.b[e];
     acc = fma(pr.a[e], bv, acc);
+    i += di, j += dj;
+    if (i >= (unsigned)n) i -= n, ++j;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -130,10 +134,13 @@ __global__ void __launch_bounds__(1024) ediis_row_kernel(EdiisBatch b, int n, do
   const double* dj = b.dj[blockIdx.x];
   const size_t n2 = (size_t)n * n;
   double acc = 0.0;
+  unsigned i = threadIdx.x % n, k = threadIdx.x / n;
+  const unsigned di = blockDim.x % n, dk = blockDim.x / n;
   for (size_t e = threadIdx.x; e < n2; e += blockDim.x) {
-    const size_t i = e % n, k = e / n;
-    const size_t et = k + i * n;
+    const size_t et = k + (size_t)i * n;
     acc = fma(b.f1[e] - fj[e], b.d1[et] - dj[et], acc);
+    i += di, k += dk;
+    if (i >= (unsigned)n) i -= n, ++k;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -289,13 +296,15 @@ int solve_orbitals(scfb_handle_s* h, scfb_scf_state* st) {
   }
   const double one = 1.0;
   SCFB_CUDA(h, cudaMemcpyAsync(st->C, st->F, n2 * ns * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  // (the spin blocks sit side by side: one left-solve covers both)
+  SCFB_BLAS(h, cublasDtrsm(st->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT,
+                           n, n * ns, &one, st->Lchol, n, st->C, n));  // A <- L^-1 F
+  h->launches += 1;
   for (int s = 0; s < ns; ++s) {
     double* A = st->C + s * n2;
-    SCFB_BLAS(h, cublasDtrsm(st->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT,
-                             n, n, &one, st->Lchol, n, A, n));  // A <- L^-1 F
     SCFB_BLAS(h, cublasDtrsm(st->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
                              n, n, &one, st->Lchol, n, A, n));  // A <- A L^-T
-    h->launches += 2;
+    h->launches += 1;
     if (st->eig_mode == 3) continue;  // both blocks are solved by one launch below
     if (st->eig_mode == 1) {
       SCFB_SOLVER(h, cusolverDnDsyevd(st->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, A, n,
@@ -344,11 +353,9 @@ int solve_orbitals(scfb_handle_s* h, scfb_scf_state* st) {
       return rc;
     SCFB_CUDA(h, cudaMemcpyAsync(st->Yprev, st->C, n2 * ns * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     st->have_y[0] = st->have_y[1] = true;
-    for (int s = 0; s < ns; ++s) {
-      SCFB_BLAS(h, cublasDtrsm(st->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, n,
-                               n, &one, st->Lchol, n, st->C + s * n2, n));  // C <- L^-T Y
-      h->launches += 1;
-    }
+    SCFB_BLAS(h, cublasDtrsm(st->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, n,
+                             n * ns, &one, st->Lchol, n, st->C, n));  // C <- L^-T Y, both blocks
+    h->launches += 1;
   }
   return SCFB_OK;
 }
