@@ -100,14 +100,24 @@ __global__ void __launch_bounds__(1024) trace_kernel(TraceBatch batch, int n, do
   const TracePair pr = batch.p[blockIdx.x];
   const size_t n2 = (size_t)n * n;
   double acc = 0.0;
-  // (i, j) of element e = i + j n advance with e: no division inside the loop
+  // (i, j) of element e = i + j n advance with e (no division inside the loop); four elements per
+  // trip so that the strided loads of the transposed operand are in flight together — the sum
+  // still runs in element order
   unsigned i = threadIdx.x % n, j = threadIdx.x / n;
   const unsigned di = blockDim.x % n, dj = blockDim.x / n;
-  for (size_t e = threadIdx.x; e < n2; e += blockDim.x) {
-    const double bv = pr.transpose_b ? pr.b[j + (size_t)i * n] : pr.b[e];
-    acc = fma(pr.a[e], bv, acc);
-    i += di, j += dj;
-    if (i >= (unsigned)n) i -= n, ++j;
+  for (size_t e = threadIdx.x; e < n2; e += 4 * (size_t)blockDim.x) {
+    double av[4], bv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t eu = e + u * (size_t)blockDim.x;
+      const bool in = eu < n2;
+      av[u] = in ? pr.a[eu] : 0.0;
+      bv[u] = in ? (pr.transpose_b ? pr.b[j + (size_t)i * n] : pr.b[eu]) : 0.0;
+      i += di, j += dj;
+      if (i >= (unsigned)n) i -= n, ++j;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc = fma(av[u], bv[u], acc);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -136,11 +146,20 @@ __global__ void __launch_bounds__(1024) ediis_row_kernel(EdiisBatch b, int n, do
   double acc = 0.0;
   unsigned i = threadIdx.x % n, k = threadIdx.x / n;
   const unsigned di = blockDim.x % n, dk = blockDim.x / n;
-  for (size_t e = threadIdx.x; e < n2; e += blockDim.x) {
-    const size_t et = k + (size_t)i * n;
-    acc = fma(b.f1[e] - fj[e], b.d1[et] - dj[et], acc);
-    i += di, k += dk;
-    if (i >= (unsigned)n) i -= n, ++k;
+  for (size_t e = threadIdx.x; e < n2; e += 4 * (size_t)blockDim.x) {
+    double fv[4], dv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t eu = e + u * (size_t)blockDim.x;
+      const size_t et = k + (size_t)i * n;
+      const bool in = eu < n2;
+      fv[u] = in ? b.f1[eu] - fj[eu] : 0.0;
+      dv[u] = in ? b.d1[et] - dj[et] : 0.0;
+      i += di, k += dk;
+      if (i >= (unsigned)n) i -= n, ++k;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc = fma(fv[u], dv[u], acc);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
