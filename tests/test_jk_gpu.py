@@ -161,6 +161,28 @@ def test_hash_family_medium(n, n_spin):
     b.close()
 
 
+@pytest.mark.parametrize("split", ["2", "4"])
+def test_split_items_fold_to_the_same_sums(split, monkeypatch):
+    """Every work item cut along b (the persistent kernel folds a group's pieces before the slab finisher):
+    dense densities against the long-double oracle, and bit-equal to nothing but itself — the order of
+    the partial sums differs from the unsplit plan, the 1e-12 gate does not."""
+    from oracle import c_oracle
+    n = 96
+    monkeypatch.setenv("SCFB_FULL_BSPLIT", split)
+    eri = c_oracle.hash_eri(n, synth.SEED_ERI)
+    rng = np.random.default_rng(int(split))
+    du, tu = rng.standard_normal((n, n, 2)), rng.standard_normal((n, n))
+    b = scf_b200.JKBuilderCUDA.synthetic(n, "hash", synth.SEED_ERI)
+    j, k = b.jk(du, tu)
+    jr, kr = c_oracle.jk_literal_ld(eri, du, tu)
+    assert rel_err(j, jr) < RTOL and rel_err(k, kr) < RTOL
+    out = np.asfortranarray(rng.standard_normal((n, n, 2)))
+    ref = out + jr[:, :, None] - kr
+    b.add_2e_term(out, du, tu)           # out += J - K through the host-pointer boundary
+    assert rel_err(out, ref) < RTOL
+    b.close()
+
+
 # ---- sharding: sum of per-rank partials == unsharded (no NCCL needed) --------------------
 @pytest.mark.parametrize("n,n_ranks", [(12, 2), (10, 4), (9, 8), (5, 8)])
 def test_shard_partials_sum_to_full(n, n_ranks):
