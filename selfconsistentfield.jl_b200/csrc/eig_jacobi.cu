@@ -3,7 +3,8 @@
 // syevd / syevj spend 1-2.5 ms in ~200 tiny launches, 3-5x the Fock build of the same step at n_bf = 128).
 //
 // One-sided (Hestenes) Jacobi with the matrix resident in shared memory — of one CTA (n <= 32) or
-// spread over a cluster of 8 CTAs that exchange column blocks through distributed shared memory:
+// spread over a cluster of 8 (n <= 320) or 16 (n <= 448) CTAs that exchange column blocks through
+// distributed shared memory:
 //
 //   U = (A / sigma + I) V0        V0 = eigenvectors of the previous SCF step (or I): U's columns are
 //                                 then nearly orthogonal already and 2-4 sweeps suffice
@@ -238,11 +239,12 @@ jacobi_eig_kernel(const double* __restrict__ AV, const double* __restrict__ V0, 
 // Every pair of columns meets exactly once per sweep, as in the one-CTA version; a round touches
 // 2 bw columns per CTA, the 8 CTAs run their rounds concurrently.
 // ------------------------------------------------------------------------------------------
+// kCluster = 16 (non-portable cluster size, opt-in per launch) halves the block width again and
+// carries the scheme to n = 448 (4 bw LD doubles per CTA must fit 226 KB).
 namespace cg = cooperative_groups;
-constexpr int kCluster = 8;
 
-template <int RPT2>
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(768, 1)
+template <int kCluster, int RPT2, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 jacobi_eig_cluster_kernel(const double* __restrict__ AV, const double* __restrict__ V0, double* __restrict__ Z,
                           double* __restrict__ W, int* __restrict__ info, int* __restrict__ sweeps_out, int n,
                           int bw, double tol) {
@@ -456,19 +458,31 @@ jacobi_eig_cluster_kernel(const double* __restrict__ AV, const double* __restric
   }
 }
 
-template <int RPT2>
+template <int CL, int RPT2, int MAXT>
 cudaError_t launch_jacobi_cluster(scfb_handle_s* h, int batch, int threads, size_t smem, const double* AV,
                                   const double* V0, double* Z, double* W, int* info, int* sweeps_out, int n, int bw,
                                   double tol) {
+  auto kernel = jacobi_eig_cluster_kernel<CL, RPT2, MAXT>;
   static thread_local int attr_dev = -1;
   if (attr_dev != h->device) {
-    cudaError_t e = cudaFuncSetAttribute(jacobi_eig_cluster_kernel<RPT2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024 - 1024);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    if (e == cudaSuccess && CL > 8) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return e;
     attr_dev = h->device;
   }
-  jacobi_eig_cluster_kernel<RPT2><<<batch * kCluster, threads, smem, h->stream>>>(AV, V0, Z, W, info, sweeps_out, n, bw, tol);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(batch * CL);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, AV, V0, Z, W, info, sweeps_out, n, bw, tol);
 }
 
 template <int RPT2>
@@ -487,7 +501,9 @@ cudaError_t launch_jacobi(scfb_handle_s* h, int batch, int threads, size_t smem,
 
 }  // namespace
 
-int scfb_jacobi_eig_max_n() { return 320; }  // cluster kernel: 4 bw LD doubles per CTA, bw = ceil(m / 16) <= 20 warps of pairs
+constexpr int kMaxN8 = 320;   // 8-CTA cluster: 4 bw LD doubles per CTA, bw = ceil(m / 16) <= 20 warps of pairs
+int scfb_jacobi_eig_max_n() { return 448; }  // 16-CTA cluster: bw = ceil(m / 32) <= 14
+int scfb_jacobi_eig_default_max_n() { return 448; }  // up to here it replaces cuSOLVER by default (dense.cu)
 
 // Eigen-decomposition of `batch` symmetric n x n matrices A_b (column-major, consecutive).
 //   AV : A_b V0_b when a warm start V0 is given, else A_b            (not modified)
@@ -505,20 +521,19 @@ int scfb_launch_jacobi_eig(scfb_handle_s* h, int n, int batch, const double* AV,
   }();
   if (n > single_max || n > 168) {
     const int LD = n + (n & 1);
-    const int bw = (LD + 2 * kCluster - 1) / (2 * kCluster);
+    const int cl = n <= kMaxN8 ? 8 : 16;
+    const int bw = (LD + 2 * cl - 1) / (2 * cl);
     const int mt = bw + (bw & 1);
     const int threads = 32 * (mt > bw ? mt : bw);
-    const size_t smem = (4 * (size_t)bw * LD + 4 * bw + 2 * kCluster * bw) * sizeof(double);
+    const size_t smem = (4 * (size_t)bw * LD + 4 * bw + 2 * cl * bw) * sizeof(double);
     const int rpt2 = (LD / 2 + 31) / 32;
     cudaError_t e;
-    if (rpt2 <= 1)
-      e = launch_jacobi_cluster<1>(h, batch, threads, smem, AV, V0, Z, W, info, sweeps_out, n, bw, tol);
-    else if (rpt2 <= 2)
-      e = launch_jacobi_cluster<2>(h, batch, threads, smem, AV, V0, Z, W, info, sweeps_out, n, bw, tol);
-    else if (rpt2 <= 3)
-      e = launch_jacobi_cluster<3>(h, batch, threads, smem, AV, V0, Z, W, info, sweeps_out, n, bw, tol);
+#define SCFB_JAC(CL, R, T) launch_jacobi_cluster<CL, R, T>(h, batch, threads, smem, AV, V0, Z, W, info, sweeps_out, n, bw, tol)
+    if (cl == 8)
+      e = rpt2 <= 1 ? SCFB_JAC(8, 1, 768) : rpt2 <= 2 ? SCFB_JAC(8, 2, 768) : rpt2 <= 3 ? SCFB_JAC(8, 3, 768) : SCFB_JAC(8, 5, 768);
     else
-      e = launch_jacobi_cluster<5>(h, batch, threads, smem, AV, V0, Z, W, info, sweeps_out, n, bw, tol);
+      e = SCFB_JAC(16, 7, 512);
+#undef SCFB_JAC
     if (e != cudaSuccess)
       return scfb_fail(h, SCFB_ERR_CUDA, "jacobi_eig_cluster_kernel launch: %s", cudaGetErrorString(e));
     h->launches += 1;

@@ -188,6 +188,7 @@ int scfb_comm_allreduce_jk(scfb_handle_s* h, int n_spin);
 int scfb_comm_destroy(scfb_handle_s* h);
 // eig_jacobi.cu
 int scfb_jacobi_eig_max_n();
+int scfb_jacobi_eig_default_max_n();
 int scfb_launch_jacobi_eig(scfb_handle_s* h, int n, int batch, const double* AV, const double* V0, double* Z, double* W,
                            int* info, int* sweeps_out);
 // dense.cu
