@@ -171,9 +171,9 @@ int scfb_pulay_error(scfb_handle_t h, int n_spin, const double* fock, const doub
                      const double* overlap, double* error_out);
 int scfb_sygvd(scfb_handle_t h, int n_spin, int n_orb, const double* fock, const double* overlap,
                double* orben_out, double* orbcoeff_out);
-/* The eigensolver scfb_scf_roothaan uses for n_bas <= 448 (one-sided Jacobi, the matrix resident in the shared
+/* The eigensolver scfb_scf_roothaan uses for n_bas <= 512 (one-sided Jacobi, the matrix resident in the shared
  * memory of one CTA or of a cluster of 8 / 16 CTAs; compute_orbitals.jl:14 after the reduction with the cached Cholesky factor of S):
- * `batch` (1 or 2) symmetric n x n matrices a (n <= 448), column-major and consecutive; v0 = NULL or orthonormal
+ * `batch` (1 or 2) symmetric n x n matrices a (n <= 512), column-major and consecutive; v0 = NULL or orthonormal
  * warm-start bases (eigenvectors of a nearby matrix).  w_out (batch*n) ascending, z_out columns = eigenvectors,
  * sweeps_out[batch] = Jacobi sweeps taken.  n is independent of the handle's n_bas. */
 int scfb_syev_jacobi(scfb_handle_t h, int n, int batch, const double* a, const double* v0, double* w_out,

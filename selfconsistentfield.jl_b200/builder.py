@@ -184,7 +184,7 @@ class JKBuilderCUDA(TwoElectronBuilder):
 
     def syev_jacobi(self, a, v0=None):
         """Eigen-decomposition of one (n, n) or a stack (batch, n, n) of symmetric matrices with the
-        small-matrix Jacobi kernels the device-resident SCF step uses (n <= 448); `v0`: orthonormal
+        small-matrix Jacobi kernels the device-resident SCF step uses (n <= 512); `v0`: orthonormal
         warm-start bases of the same shape.  Returns (w ascending, z with eigenvectors in columns, sweeps)."""
         a = np.asarray(a, dtype=np.float64)
         single = a.ndim == 2

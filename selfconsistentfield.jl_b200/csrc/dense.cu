@@ -39,7 +39,7 @@ struct scfb_scf_state {
   double* Lchol = nullptr;   // Cholesky factor of S (lower), computed once (ScfProblem.jl:48-49 TODO)
   int eig_mode = 0;          // 0 = Dsygvd per block (LAPACK path), 1 = cached Cholesky + Dsyevd,
                              // 2 = cached Cholesky + cuSOLVER Jacobi warm-started in the previous step's eigenbasis
-                             // 3 = cached Cholesky + the shared-memory / cluster Jacobi of eig_jacobi.cu (n <= 448)
+                             // 3 = cached Cholesky + the shared-memory / cluster Jacobi of eig_jacobi.cu (n <= 512)
   double* Uj = nullptr;      // 2 n^2: (L^-1 F L^-T) Yprev, the input of mode 3
   int* jsweeps = nullptr;    // 2 ints: sweeps the last mode-3 solve took per spin block
   double* work_ev = nullptr;  // Dsyevd / Dsyevj workspace
@@ -453,9 +453,9 @@ int scfb_scf_setup(scfb_handle_t h, const double* overlap, const double* h_core,
   {
     const char* eig = std::getenv("SCFB_EIG");
     // default (same-box timings in profiles/README.md): the warm-started Jacobi kernels of eig_jacobi.cu up to
-    // n_bf = 448, Dsyevd on the cached factor beyond.  RHF iteration at n_bf = 128: Dsygvd 3.5 ms, Dsyevd on the
+    // n_bf = 512, Dsyevd on the cached factor beyond.  RHF iteration at n_bf = 128: Dsygvd 3.5 ms, Dsyevd on the
     // cached factor 3.6, cuSOLVER's Jacobi warm-started 2.4, eig_jacobi.cu 1.3; at n_bf = 256: Dsyevd 8.3, eig_jacobi.cu 7.7;
-    // at n_bf = 384 (packed8): Dsyevd 9.6, eig_jacobi.cu 7.8.
+    // at n_bf = 384 (packed8): Dsyevd 9.6, eig_jacobi.cu 7.8; at n_bf = 512 (packed8): 19.9 / 19.1.
     const int native_ok = n <= scfb_jacobi_eig_max_n();
     want_eig = !eig ? (n <= scfb_jacobi_eig_default_max_n() ? 3 : 1)
                     : (std::strcmp(eig, "syevd") == 0 ? 1

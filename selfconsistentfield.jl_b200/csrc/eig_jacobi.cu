@@ -3,7 +3,7 @@
 // syevd / syevj spend 1-2.5 ms in ~200 tiny launches, 3-5x the Fock build of the same step at n_bf = 128).
 //
 // One-sided (Hestenes) Jacobi with the matrix resident in shared memory — of one CTA (n <= 32) or
-// spread over a cluster of 8 (n <= 320) or 16 (n <= 448) CTAs that exchange column blocks through
+// spread over a cluster of 8 (n <= 320) or 16 (n <= 512) CTAs that exchange column blocks through
 // distributed shared memory:
 //
 //   U = (A / sigma + I) V0        V0 = eigenvectors of the previous SCF step (or I): U's columns are
@@ -240,10 +240,14 @@ jacobi_eig_kernel(const double* __restrict__ AV, const double* __restrict__ V0, 
 // 2 bw columns per CTA, the 8 CTAs run their rounds concurrently.
 // ------------------------------------------------------------------------------------------
 // kCluster = 16 (non-portable cluster size, opt-in per launch) halves the block width again and
-// carries the scheme to n = 448 (4 bw LD doubles per CTA must fit 226 KB).
+// carries the scheme to n = 448 (4 bw LD doubles per CTA must fit 226 KB).  TRIPLE keeps THREE block
+// buffers per CTA instead of four (n <= 512: 3 x 64 KB): an exchange is then two phases — (1) L
+// blocks (R of rank 0) go into the right neighbour's spare buffer, barrier, (2) R blocks go into the
+// left neighbour's just-vacated L buffer (rank 0: its vacated R buffer), barrier — after which the
+// roles rotate (L <- spare, R <- old L, spare <- old R) identically in every CTA but rank 0.
 namespace cg = cooperative_groups;
 
-template <int kCluster, int RPT2, int MAXT>
+template <int kCluster, int RPT2, int MAXT, bool TRIPLE>
 __global__ void __launch_bounds__(MAXT, 1)
 jacobi_eig_cluster_kernel(const double* __restrict__ AV, const double* __restrict__ V0, double* __restrict__ Z,
                           double* __restrict__ W, int* __restrict__ info, int* __restrict__ sweeps_out, int n,
@@ -254,9 +258,10 @@ jacobi_eig_cluster_kernel(const double* __restrict__ AV, const double* __restric
   const int LD = n + (n & 1), half = LD >> 1;
   const int bsz = bw * LD;  // doubles per block
   extern __shared__ __align__(16) double sm[];
-  double* blk = sm;                         // [2 buffers][2 slots][bw][LD]
-  double* nrm = sm + 4 * (size_t)bsz;       // [2 buffers][2 slots][bw] squared norms
-  double* lam_all = nrm + 4 * bw;           // [16 bw] gathered column norms (end)
+  constexpr int NBUF = TRIPLE ? 3 : 4;
+  double* blk = sm;                         // [NBUF block buffers][bw][LD]  (double-buffered: [2][2 slots])
+  double* nrm = sm + NBUF * (size_t)bsz;    // [NBUF][bw] squared norms travelling with the blocks
+  double* lam_all = nrm + NBUF * bw;        // [2 kCluster bw] gathered column norms (end)
   __shared__ double red[32];
   __shared__ double part[kCluster];
   __shared__ int flags[kCluster];
@@ -300,7 +305,9 @@ jacobi_eig_cluster_kernel(const double* __restrict__ AV, const double* __restric
   const int g = warp;                 // one warp per column pair
   const int mt = bw + (bw & 1);       // players of the intra-block tournament (odd bw: one bye)
   const double tol2 = tol * tol;
-  int cur = 0;
+  // physical buffers of the resident L and R blocks (and, TRIPLE, of the spare) — of the ranks >= 1;
+  // rank 0 of the TRIPLE scheme keeps L in buffer 0 and receives every R in buffer 1
+  int iL = 0, iR = 1, iS = 2;
 
   // rotate columns x, y (local shared memory) with cached squared norms *na, *nb
   auto do_pair = [&](double* xc, double* yc, double* na, double* nb, int& big) {
@@ -345,24 +352,37 @@ jacobi_eig_cluster_kernel(const double* __restrict__ AV, const double* __restric
       }
     }
   };
+  // block copy into (possibly remote) shared memory, with the block's cached norms
+  auto push = [&](int src_buf, int dst_rank, int dst_buf) {
+    double2* d = reinterpret_cast<double2*>(cl.map_shared_rank(blk, dst_rank) + (size_t)dst_buf * bsz);
+    const double2* sp = reinterpret_cast<const double2*>(blk + (size_t)src_buf * bsz);
+    for (int i = tid; i < bsz / 2; i += nt) d[i] = sp[i];
+    if (tid < bw) cl.map_shared_rank(nrm, dst_rank)[dst_buf * bw + tid] = nrm[src_buf * bw + tid];
+  };
 
   int sweep = 0;
   bool converged = false;
   for (; sweep < kMaxSweeps; ++sweep) {
     int big = 0;
-    double* B = blk + (size_t)cur * 2 * bsz;   // [slot][bw][LD]
-    double* N = nrm + cur * 2 * bw;            // [slot][bw]
+    const bool fixed0 = TRIPLE && rank == 0;
+    double* BL = blk + (size_t)(fixed0 ? 0 : iL) * bsz;
+    double* BR = blk + (size_t)(fixed0 ? 1 : iR) * bsz;
+    double* NL = nrm + (fixed0 ? 0 : iL) * bw;
+    double* NR = nrm + (fixed0 ? 1 : iR) * bw;
     // fresh squared norms of the 2 bw resident columns
     for (int j = warp; j < 2 * bw; j += nwarps) {
+      const double* col = (j < bw ? BL + (size_t)j * LD : BR + (size_t)(j - bw) * LD);
       double s = 0.0;
-      for (int row = lane; row < LD; row += 32) s = fma(B[(size_t)j * LD + row], B[(size_t)j * LD + row], s);
+      for (int row = lane; row < LD; row += 32) s = fma(col[row], col[row], s);
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) N[j] = s;
+      if (lane == 0) (j < bw ? NL[j] : NR[j - bw]) = s;
     }
     __syncthreads();
     // intra-block tournament: warps [0, mt/2) work on L, [mt/2, mt) on R
     {
       const int slot = g / (mt >> 1), pi = g - slot * (mt >> 1);
+      double* B = slot ? BR : BL;
+      double* N = slot ? NR : NL;
       for (int r = 0; r < mt - 1; ++r) {
         if (g < mt) {
           int p = mt - 1, q = r;
@@ -372,21 +392,19 @@ jacobi_eig_cluster_kernel(const double* __restrict__ AV, const double* __restric
             q = r - pi;
             if (q < 0) q += mt - 1;
           }
-          if (p < bw && q < bw)
-            do_pair(B + (size_t)(slot * bw + p) * LD, B + (size_t)(slot * bw + q) * LD, N + slot * bw + p,
-                    N + slot * bw + q, big);
+          if (p < bw && q < bw) do_pair(B + (size_t)p * LD, B + (size_t)q * LD, N + p, N + q, big);
         }
         __syncthreads();
       }
     }
     for (int step = 0; step < 2 * kCluster - 1; ++step) {
-      B = blk + (size_t)cur * 2 * bsz;
-      N = nrm + cur * 2 * bw;
+      BL = blk + (size_t)(fixed0 ? 0 : iL) * bsz, BR = blk + (size_t)(fixed0 ? 1 : iR) * bsz;
+      NL = nrm + (fixed0 ? 0 : iL) * bw, NR = nrm + (fixed0 ? 1 : iR) * bw;
       for (int r = 0; r < bw; ++r) {
         if (g < bw) {
           int q = g + r;
           if (q >= bw) q -= bw;
-          do_pair(B + (size_t)g * LD, B + (size_t)(bw + q) * LD, N + g, N + bw + q, big);
+          do_pair(BL + (size_t)g * LD, BR + (size_t)q * LD, NL + g, NR + q, big);
         }
         __syncthreads();
       }
@@ -394,26 +412,32 @@ jacobi_eig_cluster_kernel(const double* __restrict__ AV, const double* __restric
         const int any = __syncthreads_or(big);
         if (tid < kCluster) cl.map_shared_rank(flags, tid)[rank] = any;
       }
-      // push: L_0 stays, R_0 -> L_1, L_k -> L_k+1, R_k -> R_k-1, L_7 -> R_7   (into the spare buffers)
-      const int nxt = cur ^ 1;
-      const int dstL_rank = rank == 0 ? 0 : (rank == kCluster - 1 ? rank : rank + 1);
-      const int dstL_slot = rank == kCluster - 1 ? 1 : 0;
-      const int dstR_rank = rank == 0 ? 1 : rank - 1;
-      const int dstR_slot = rank == 0 ? 0 : 1;
-      double2* dl = reinterpret_cast<double2*>(cl.map_shared_rank(blk, dstL_rank) + ((size_t)nxt * 2 + dstL_slot) * bsz);
-      double2* dr = reinterpret_cast<double2*>(cl.map_shared_rank(blk, dstR_rank) + ((size_t)nxt * 2 + dstR_slot) * bsz);
-      const double2* sl = reinterpret_cast<const double2*>(B);
-      const double2* sr = reinterpret_cast<const double2*>(B + bsz);
-      for (int i = tid; i < bsz / 2; i += nt) {
-        dl[i] = sl[i];
-        dr[i] = sr[i];
+      // round-robin of the blocks: L_0 stays, R_0 -> L_1, L_k -> L_k+1, R_k -> R_k-1, L_last -> R_last
+      if (!TRIPLE) {  // into the other half of the double buffer, one barrier
+        const int nL = iL ^ 2, nR = iR ^ 2;
+        if (rank == 0) {
+          push(iL, 0, nL);
+          push(iR, 1, nL);
+        } else {
+          push(iL, rank == kCluster - 1 ? rank : rank + 1, rank == kCluster - 1 ? nR : nL);
+          push(iR, rank - 1, nR);
+        }
+        cl.sync();
+        iL = nL, iR = nR;
+      } else {
+        if (rank == 0)
+          push(1, 1, iS);
+        else if (rank < kCluster - 1)
+          push(iL, rank + 1, iS);
+        cl.sync();
+        if (rank == 1)
+          push(iR, 0, 1);
+        else if (rank > 1)
+          push(iR, rank - 1, iL);
+        cl.sync();
+        const int oL = iL, oR = iR;
+        iL = iS, iR = oL, iS = oR;
       }
-      if (tid < bw) {
-        cl.map_shared_rank(nrm, dstL_rank)[(nxt * 2 + dstL_slot) * bw + tid] = N[tid];
-        cl.map_shared_rank(nrm, dstR_rank)[(nxt * 2 + dstR_slot) * bw + tid] = N[bw + tid];
-      }
-      cl.sync();
-      cur = nxt;
     }
     int any = 0;
     for (int r = 0; r < kCluster; ++r) any |= flags[r];
@@ -422,14 +446,17 @@ jacobi_eig_cluster_kernel(const double* __restrict__ AV, const double* __restric
       ++sweep;
       break;
     }
-    // (the next verdict is written 15 cluster barriers from here: nobody can still be reading this one)
+    // (the next verdict is written 15+ cluster barriers from here: nobody can still be reading this one)
   }
 
   // ---- norms of the resident columns, all-gathered; rank among all real columns; write out ----
-  double* B = blk + (size_t)cur * 2 * bsz;
+  const bool fixed0 = TRIPLE && rank == 0;
+  const double* BL = blk + (size_t)(fixed0 ? 0 : iL) * bsz;
+  const double* BR = blk + (size_t)(fixed0 ? 1 : iR) * bsz;
   for (int j = warp; j < 2 * bw; j += nwarps) {
+    const double* col = (j < bw ? BL + (size_t)j * LD : BR + (size_t)(j - bw) * LD);
     double s = 0.0;
-    for (int row = lane; row < LD; row += 32) s = fma(B[(size_t)j * LD + row], B[(size_t)j * LD + row], s);
+    for (int row = lane; row < LD; row += 32) s = fma(col[row], col[row], s);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const double nj = sqrt(s);  // 0 exactly for the phantom columns (real ones are >= 1/3)
     for (int r = lane; r < kCluster; r += 32) cl.map_shared_rank(lam_all, r)[rank * 2 * bw + j] = nj;
@@ -449,7 +476,8 @@ jacobi_eig_cluster_kernel(const double* __restrict__ AV, const double* __restric
     }
     for (int o = 16; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
     const double inv = 1.0 / nj;
-    for (int row = lane; row < n; row += 32) Zb[(size_t)rk * n + row] = B[(size_t)j * LD + row] * inv;
+    const double* col = (j < bw ? BL + (size_t)j * LD : BR + (size_t)(j - bw) * LD);
+    for (int row = lane; row < n; row += 32) Zb[(size_t)rk * n + row] = col[row] * inv;
     if (lane == 0) Wb[rk] = sigma * (nj - 1.0);
   }
   if (tid == 0 && rank == 0) {
@@ -458,11 +486,11 @@ jacobi_eig_cluster_kernel(const double* __restrict__ AV, const double* __restric
   }
 }
 
-template <int CL, int RPT2, int MAXT>
+template <int CL, int RPT2, int MAXT, bool TRIPLE>
 cudaError_t launch_jacobi_cluster(scfb_handle_s* h, int batch, int threads, size_t smem, const double* AV,
                                   const double* V0, double* Z, double* W, int* info, int* sweeps_out, int n, int bw,
                                   double tol) {
-  auto kernel = jacobi_eig_cluster_kernel<CL, RPT2, MAXT>;
+  auto kernel = jacobi_eig_cluster_kernel<CL, RPT2, MAXT, TRIPLE>;
   static thread_local int attr_dev = -1;
   if (attr_dev != h->device) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
@@ -502,8 +530,9 @@ cudaError_t launch_jacobi(scfb_handle_s* h, int batch, int threads, size_t smem,
 }  // namespace
 
 constexpr int kMaxN8 = 320;   // 8-CTA cluster: 4 bw LD doubles per CTA, bw = ceil(m / 16) <= 20 warps of pairs
-int scfb_jacobi_eig_max_n() { return 448; }  // 16-CTA cluster: bw = ceil(m / 32) <= 14
-int scfb_jacobi_eig_default_max_n() { return 448; }  // up to here it replaces cuSOLVER by default (dense.cu)
+constexpr int kMaxN16 = 448;  // 16-CTA cluster, double-buffered: bw = ceil(m / 32) <= 14
+int scfb_jacobi_eig_max_n() { return 512; }  // 16-CTA cluster, three block buffers: bw <= 16, 3 x 64 KB
+int scfb_jacobi_eig_default_max_n() { return 512; }  // up to here it replaces cuSOLVER by default (dense.cu)
 
 // Eigen-decomposition of `batch` symmetric n x n matrices A_b (column-major, consecutive).
 //   AV : A_b V0_b when a warm start V0 is given, else A_b            (not modified)
@@ -522,17 +551,25 @@ int scfb_launch_jacobi_eig(scfb_handle_s* h, int n, int batch, const double* AV,
   if (n > single_max || n > 168) {
     const int LD = n + (n & 1);
     const int cl = n <= kMaxN8 ? 8 : 16;
+    const bool triple = n > kMaxN16;
     const int bw = (LD + 2 * cl - 1) / (2 * cl);
     const int mt = bw + (bw & 1);
     const int threads = 32 * (mt > bw ? mt : bw);
-    const size_t smem = (4 * (size_t)bw * LD + 4 * bw + 2 * cl * bw) * sizeof(double);
+    const int nbuf = triple ? 3 : 4;
+    const size_t smem = (nbuf * (size_t)bw * LD + nbuf * bw + 2 * cl * bw) * sizeof(double);
     const int rpt2 = (LD / 2 + 31) / 32;
     cudaError_t e;
-#define SCFB_JAC(CL, R, T) launch_jacobi_cluster<CL, R, T>(h, batch, threads, smem, AV, V0, Z, W, info, sweeps_out, n, bw, tol)
+#define SCFB_JAC(CL, R, T, TR) \
+  launch_jacobi_cluster<CL, R, T, TR>(h, batch, threads, smem, AV, V0, Z, W, info, sweeps_out, n, bw, tol)
     if (cl == 8)
-      e = rpt2 <= 1 ? SCFB_JAC(8, 1, 768) : rpt2 <= 2 ? SCFB_JAC(8, 2, 768) : rpt2 <= 3 ? SCFB_JAC(8, 3, 768) : SCFB_JAC(8, 5, 768);
+      e = rpt2 <= 1   ? SCFB_JAC(8, 1, 768, false)
+          : rpt2 <= 2 ? SCFB_JAC(8, 2, 768, false)
+          : rpt2 <= 3 ? SCFB_JAC(8, 3, 768, false)
+                      : SCFB_JAC(8, 5, 768, false);
+    else if (!triple)
+      e = SCFB_JAC(16, 7, 512, false);
     else
-      e = SCFB_JAC(16, 7, 512);
+      e = SCFB_JAC(16, 8, 512, true);
 #undef SCFB_JAC
     if (e != cudaSuccess)
       return scfb_fail(h, SCFB_ERR_CUDA, "jacobi_eig_cluster_kernel launch: %s", cudaGetErrorString(e));

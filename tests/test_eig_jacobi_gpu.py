@@ -3,8 +3,8 @@ scfb_syev_jacobi) against LAPACK (numpy.linalg.eigh — what compute_orbitals.jl
 reduction to standard form): eigenvalues, residuals, orthonormality, ordering; cold and warm starts;
 every shape class of the kernels (odd n -> phantom column / row, n <= 64 -> one CTA with the matrix in
 shared memory, n >= 65 -> a cluster of 8 CTAs exchanging column blocks over distributed shared memory,
-block widths with and without a bye in the intra-block tournament, n > 320 -> a cluster of 16, n = 448 ->
-the size limit)."""
+block widths with and without a bye in the intra-block tournament, n > 320 -> a cluster of 16, n > 448 -> three block buffers per CTA
+and a two-phase exchange, n = 512 -> the size limit)."""
 import numpy as np
 import pytest
 
@@ -35,7 +35,7 @@ def check(a, w, z, tol=1e-12):
     assert np.abs(z.T @ z - np.eye(n)).max() <= tol
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 16, 31, 32, 33, 63, 64, 65, 100, 127, 128, 129, 167, 168, 169, 200, 255, 256, 320, 321, 383, 384, 448])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 16, 31, 32, 33, 63, 64, 65, 100, 127, 128, 129, 167, 168, 169, 200, 255, 256, 320, 321, 383, 384, 448, 449, 500, 511, 512])
 def test_cold_start_matches_lapack(builder, n):
     rng = np.random.default_rng(n)
     a = sym(rng, n)
@@ -61,7 +61,7 @@ def test_batch_of_two_and_fock_like_spectrum(builder):
         check(a[b], w[b], z[b])
 
 
-@pytest.mark.parametrize("n", [24, 127, 128, 168, 256])
+@pytest.mark.parametrize("n", [24, 127, 128, 168, 256, 384, 512])
 def test_warm_start_takes_fewer_sweeps(builder, n):
     rng = np.random.default_rng(100 + n)
     a = sym(rng, n)
@@ -106,4 +106,4 @@ def test_scale_invariance(builder, scale):
 
 def test_rejects_matrices_beyond_the_size_limit(builder):
     with pytest.raises(scf_b200.ScfbError):
-        builder.syev_jacobi(np.eye(449))
+        builder.syev_jacobi(np.eye(513))
