@@ -128,6 +128,11 @@ int scfb_last_build_ms(scfb_handle_t h, double* stream_ms, double* total_ms);
 int scfb_build_ms_history(scfb_handle_t h, int max_builds, double* stream_ms, double* total_ms, int* n_builds);
 /* Number of kernels this library launched on this handle since creation. */
 int scfb_launch_count(scfb_handle_t h, uint64_t* launches);
+/* Introspection (no device needed): how the full-layout kernel cuts a shard of n_slabs nu-slabs into work
+ * items on a device with n_sm SMs.  plan6 = { persistent TMA kernel? , slabs handed out as whole (nu, c-chunk)
+ * items, pieces the remaining slabs' items are cut into along b (LDG kernel: every item), partial K rows,
+ * partial J rows, split (nu, c-chunk) groups }. */
+int scfb_full_plan_query(int n_bas, int n_slabs, int n_sm, int* plan6);
 
 /* ---- device-resident SCF step (rows a4-a9 of SURVEY.md 8) ---------------------------
  * The handle keeps S, h_core, the density, the Fock iterate, the Pulay error, the orbitals

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "scfb_last_build_ms": [_h, _dp, _dp],
     "scfb_build_ms_history": [_h, C.c_int, _dp, _dp, C.POINTER(C.c_int)],
     "scfb_launch_count": [_h, C.POINTER(C.c_uint64)],
+    "scfb_full_plan_query": [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)],
     "scfb_scf_setup": [_h, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
     "scfb_scf_n_spin": [_h, C.POINTER(C.c_int)],
     "scfb_scf_n_densities": [_h, C.POINTER(C.c_int)],

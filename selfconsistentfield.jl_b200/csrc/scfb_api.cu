@@ -515,6 +515,18 @@ int scfb_jk_split(scfb_handle_t h, int n_spin, const double* density, const doub
   return scfb_peer_check(h);
 }
 
+int scfb_full_plan_query(int n_bas, int n_slabs, int n_sm, int* plan6) {
+  if (!plan6 || n_bas < 1 || n_slabs < 0) return scfb_fail(nullptr, SCFB_ERR_ARG, "bad arguments");
+  const ScfbFullPlan pl = scfb_full_plan(n_bas, n_slabs, n_sm);
+  plan6[0] = pl.tma ? 1 : 0;
+  plan6[1] = pl.tma ? pl.whole_slabs : n_slabs;
+  plan6[2] = pl.tma ? pl.tail_bs : pl.b_splits;
+  plan6[3] = (int)pl.kpart_rows;
+  plan6[4] = (int)pl.jpart_rows;
+  plan6[5] = pl.n_groups;
+  return SCFB_OK;
+}
+
 int scfb_last_build_ms(scfb_handle_t h, double* stream_ms, double* total_ms) {
   if (int rc = check_handle(h)) return rc;
   if (h->build_no == 0) return scfb_fail(h, SCFB_ERR_STATE, "no build has run on this handle");
