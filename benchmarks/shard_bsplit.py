@@ -1,6 +1,6 @@
 """Time one rank's shard of the full-layout Fock build on a single GPU (no exchange), e.g. the
 1/8 shard of n_bf=256 that each GPU of an 8-GPU run streams.  Used to tune the b-split rule
-(SCFB_FULL_BSPLIT overrides csrc/jk_full.cu:scfb_full_b_splits; one process per setting because the
+(SCFB_FULL_BSPLIT / SCFB_FULL_TAIL override csrc/jk_full.cu:scfb_full_plan; one process per setting because the
 override is read once).   python benchmarks/shard_bsplit.py --n-bas 256 --ranks 8 --rank 5"""
 import argparse
 import os

@@ -272,7 +272,7 @@ def test_wide_rows_known_answers_on_a_shard(n, n_ranks):
                                               (64, 0, "2", "1"), (128, 3, None, "0"), (64, 1, "2", "0")])
 def test_eighth_shard_with_b_splits_known_answers(n, rank, split, tma, monkeypatch):
     """What one GPU of eight runs at n_bf=256 / 128, with the work items split along b
-    (csrc/jk_full.cu scfb_full_b_splits: the LDG kernel's rule, forced for the TMA kernel): J
+    (csrc/jk_full.cu scfb_full_plan: the LDG kernel's rule, forced for the TMA kernel whose default splits only the tail): J
     becomes a per-CTA partial too and the persistent kernel's queue hands out chunk x slab x split
     items.  Unit densities pin the owned columns bit for bit (UHF: both K accumulators)."""
     monkeypatch.setenv("SCFB_FULL_TMA", tma)           # both read when the handle is created / launched
